@@ -1,0 +1,445 @@
+// GF(2^255-19) arithmetic for the Ed25519 kernels — 8 x 32-bit saturated limbs, one element per thread.
+//
+// Replaces the field layer under Go's crypto/ed25519 (crypto/internal/fips140/edwards25519/field, 5x51-bit
+// limbs on amd64) that the reference reaches from vc_service.go:463,504.  B200 has no 64x64 multiplier: a
+// 51-bit limb product costs four 32-bit IMADs, so the native radix here is 2^32 — 64 IMAD.WIDE.U32 per
+// multiplication issued as carry chains (mad.lo.cc / madc.hi.cc) over separate even- and odd-column
+// accumulators, so no carry ever crosses between two chains and each chain is a straight run of
+// dependent-by-carry-flag-only instructions.  (north_star suggests 51-bit limbs spread over lanes with
+// warp shuffles; thread-per-credential with 32-bit limbs keeps all 64 partial products in one thread's
+// registers and needs no shuffles — see DESIGN.md "deviations".)
+//
+// Representation: any value in [0, 2^256) stands for its residue mod p ("weakly reduced").  2^256 = 38
+// (mod p).  fe_tobytes produces the unique canonical encoding.
+#pragma once
+#include "afc_common.cuh"
+
+#ifndef AFC_FE_PTX
+#define AFC_FE_PTX 1
+#endif
+
+namespace afc {
+
+struct alignas(16) fe { uint32_t v[8]; };
+
+AFC_HD void fe_0(fe& h) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = 0;
+}
+AFC_HD void fe_1(fe& h) { fe_0(h); h.v[0] = 1; }
+AFC_HD void fe_copy(fe& h, const fe& f) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = f.v[i];
+}
+AFC_HD void fe_from_words(fe& h, const uint32_t* w) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = w[i];
+}
+
+
+// ---------------------------------------------------------------------------------- portable variants
+// Plain-C versions of every primitive: the reference the PTX paths are checked against on the device
+// (afc_selftest) and the code tests/hostsim runs on the CPU.
+AFC_HD void fe_add_c(fe& h, const fe& f, const fe& g) {
+    uint64_t c = 0;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)f.v[i] + g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+    c *= 38;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    r[0] += (uint32_t)c * 38u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+}
+AFC_HD void fe_sub_c(fe& h, const fe& f, const fe& g) {
+    int64_t c = 0;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (int64_t)f.v[i] - g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+    int64_t k = (c < 0) ? 38 : 0;
+    c = -k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    if (c < 0) r[0] -= 38u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+}
+AFC_HD void fe_fold16_c(fe& h, const uint32_t* t) {
+    uint64_t c = 0;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (uint64_t)t[8 + i] * 38u; r[i] = (uint32_t)c; c >>= 32; }
+    c *= 38;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    r[0] += (uint32_t)c * 38u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+}
+AFC_HD void fe_mul_wide_c(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a[j] * b[i] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+        t[i + 8] = (uint32_t)c;
+    }
+}
+// t = a^2: off-diagonal products once (28), doubled, plus the 8 diagonal squares
+AFC_HD void fe_sq_wide_c(uint32_t* t, const uint32_t* a) {
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = i + 1; j < 8; j++) { c += (uint64_t)a[i] * a[j] + s[i + j]; s[i + j] = (uint32_t)c; c >>= 32; }
+        s[i + 8] = (uint32_t)c;
+    }
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] * a[i];
+        uint32_t lo2 = (s[2 * i] << 1) | (i ? (s[2 * i - 1] >> 31) : 0u);
+        uint32_t hi2 = (s[2 * i + 1] << 1) | (s[2 * i] >> 31);
+        c += (uint64_t)lo2 + (uint32_t)d;
+        t[2 * i] = (uint32_t)c; c >>= 32;
+        c += (uint64_t)hi2 + (uint32_t)(d >> 32);
+        t[2 * i + 1] = (uint32_t)c; c >>= 32;
+    }
+}
+AFC_HD void fe_mul_c(fe& h, const fe& f, const fe& g) { uint32_t t[16]; fe_mul_wide_c(t, f.v, g.v); fe_fold16_c(h, t); }
+AFC_HD void fe_sq_c(fe& h, const fe& f) { uint32_t t[16]; fe_sq_wide_c(t, f.v); fe_fold16_c(h, t); }
+
+// ---------------------------------------------------------------------------------- add / sub
+// h = f + g  (mod 2^256-38, weakly reduced)
+AFC_HD void fe_add(fe& h, const fe& f, const fe& g) {
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(c)
+        : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+          "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+    uint32_t k = c * 38u, c2;
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(c2)
+        : "r"(k));
+    r0 += c2 * 38u;     // second wrap leaves a value < 38: cannot carry
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    fe_add_c(h, f, g);
+#endif
+}
+
+// h = f - g  (mod 2^256-38, weakly reduced)
+AFC_HD void fe_sub(fe& h, const fe& f, const fe& g) {
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, b;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"            // 0 or 0xffffffff
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(b)
+        : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+          "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+    uint32_t k = b & 38u, b2;
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.cc.u32 %7, %7, 0;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(b2)
+        : "r"(k));
+    r0 -= b2 & 38u;     // second wrap leaves a value >= 2^256-38: cannot borrow
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    fe_sub_c(h, f, g);
+#endif
+}
+
+AFC_HD void fe_neg(fe& h, const fe& f) { fe z; fe_0(z); fe_sub(h, z, f); }
+AFC_HD void fe_dbl(fe& h, const fe& f) { fe_add(h, f, f); }
+
+// ---------------------------------------------------------------------------------- 512 -> 256 fold
+// h = (t[0..7] + 38 * t[8..15]) mod 2^256-38, weakly reduced
+AFC_HD void fe_fold16(fe& h, const uint32_t* t) {
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+    uint32_t r0 = t[0], r1 = t[1], r2 = t[2], r3 = t[3], r4 = t[4], r5 = t[5], r6 = t[6], r7 = t[7], ce;
+    const uint32_t k38 = 38u;
+    // even columns of 38*hi accumulate in place (aligned pairs), one chain
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(ce)
+        : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(k38));
+    // odd columns: fresh products at limbs (1,2) (3,4) (5,6) (7,8)
+    uint32_t o0, o1, o2, o3, o4, o5, o6, o7;
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;\n\t"
+        : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3), "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7)
+        : "r"(t[9]), "r"(t[11]), "r"(t[13]), "r"(t[15]), "r"(k38));
+    uint32_t top;
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %15, %16;\n\t"
+        : "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(top)
+        : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7), "r"(ce));
+    uint32_t k = top * 38u, c2;          // top <= 39
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(c2)
+        : "r"(k));
+    r0 += c2 * 38u;
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    fe_fold16_c(h, t);
+#endif
+}
+
+// ---------------------------------------------------------------------------------- multiply
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+// acc[0..7] += {x0,x1,x2,x3} * b at pairs (0,1)(2,3)(4,5)(6,7); carry-out -> top (fresh limb)
+#define AFC_CHAIN_ACC_TOP(a0, a1, a2, a3, a4, a5, a6, a7, top, x0, x1, x2, x3, b)                     \
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"                                                          \
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                                         \
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"                                                        \
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                                        \
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"                                                        \
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                                        \
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"                                                        \
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                                        \
+        "addc.u32 %8, 0, 0;\n\t"                                                                      \
+        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "=r"(top)   \
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b))
+// acc[0..6] += ... ; the last product's high half lands in a fresh limb a7
+#define AFC_CHAIN_ACC_NEW(a0, a1, a2, a3, a4, a5, a6, a7, x0, x1, x2, x3, b)                          \
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"                                                          \
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"                                                         \
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"                                                         \
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"                                                         \
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"                                                        \
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"                                                        \
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"                                                        \
+        "madc.hi.u32 %7, %11, %12, 0;\n\t"                                                            \
+        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "=r"(a7)              \
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b))
+// fresh products, no carries
+#define AFC_ROW_FRESH(a0, a1, a2, a3, a4, a5, a6, a7, x0, x1, x2, x3, b)                              \
+    asm("mul.lo.u32 %0, %8, %12;\n\t"                                                                 \
+        "mul.hi.u32 %1, %8, %12;\n\t"                                                                 \
+        "mul.lo.u32 %2, %9, %12;\n\t"                                                                 \
+        "mul.hi.u32 %3, %9, %12;\n\t"                                                                 \
+        "mul.lo.u32 %4, %10, %12;\n\t"                                                                \
+        "mul.hi.u32 %5, %10, %12;\n\t"                                                                \
+        "mul.lo.u32 %6, %11, %12;\n\t"                                                                \
+        "mul.hi.u32 %7, %11, %12;\n\t"                                                                \
+        : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(a4), "=r"(a5), "=r"(a6), "=r"(a7)              \
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b))
+#endif
+
+// t[0..15] = a * b (full 512-bit product)
+AFC_HD void fe_mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+    // E[k] holds limb k (even-column products: i+j even); O[k] holds limb k+1 (odd-column products)
+    uint32_t E[16], O[15];
+    AFC_ROW_FRESH(E[0], E[1], E[2], E[3], E[4], E[5], E[6], E[7], a[0], a[2], a[4], a[6], b[0]);
+    AFC_ROW_FRESH(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], a[1], a[3], a[5], a[7], b[0]);
+    E[8] = 0;
+    // row 1 (odd): E takes odd j at E[2..9] (E[9] fresh); O takes even j at O[0..7], top O[8]
+    AFC_CHAIN_ACC_NEW(E[2], E[3], E[4], E[5], E[6], E[7], E[8], E[9], a[1], a[3], a[5], a[7], b[1]);
+    AFC_CHAIN_ACC_TOP(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], O[8], a[0], a[2], a[4], a[6], b[1]);
+    // row 2 (even): E takes even j at E[2..9], top E[10]; O takes odd j at O[2..9] (O[9] fresh)
+    AFC_CHAIN_ACC_TOP(E[2], E[3], E[4], E[5], E[6], E[7], E[8], E[9], E[10], a[0], a[2], a[4], a[6], b[2]);
+    AFC_CHAIN_ACC_NEW(O[2], O[3], O[4], O[5], O[6], O[7], O[8], O[9], a[1], a[3], a[5], a[7], b[2]);
+    // row 3
+    AFC_CHAIN_ACC_NEW(E[4], E[5], E[6], E[7], E[8], E[9], E[10], E[11], a[1], a[3], a[5], a[7], b[3]);
+    AFC_CHAIN_ACC_TOP(O[2], O[3], O[4], O[5], O[6], O[7], O[8], O[9], O[10], a[0], a[2], a[4], a[6], b[3]);
+    // row 4
+    AFC_CHAIN_ACC_TOP(E[4], E[5], E[6], E[7], E[8], E[9], E[10], E[11], E[12], a[0], a[2], a[4], a[6], b[4]);
+    AFC_CHAIN_ACC_NEW(O[4], O[5], O[6], O[7], O[8], O[9], O[10], O[11], a[1], a[3], a[5], a[7], b[4]);
+    // row 5
+    AFC_CHAIN_ACC_NEW(E[6], E[7], E[8], E[9], E[10], E[11], E[12], E[13], a[1], a[3], a[5], a[7], b[5]);
+    AFC_CHAIN_ACC_TOP(O[4], O[5], O[6], O[7], O[8], O[9], O[10], O[11], O[12], a[0], a[2], a[4], a[6], b[5]);
+    // row 6
+    AFC_CHAIN_ACC_TOP(E[6], E[7], E[8], E[9], E[10], E[11], E[12], E[13], E[14], a[0], a[2], a[4], a[6], b[6]);
+    AFC_CHAIN_ACC_NEW(O[6], O[7], O[8], O[9], O[10], O[11], O[12], O[13], a[1], a[3], a[5], a[7], b[6]);
+    // row 7
+    AFC_CHAIN_ACC_NEW(E[8], E[9], E[10], E[11], E[12], E[13], E[14], E[15], a[1], a[3], a[5], a[7], b[7]);
+    AFC_CHAIN_ACC_TOP(O[6], O[7], O[8], O[9], O[10], O[11], O[12], O[13], O[14], a[0], a[2], a[4], a[6], b[7]);
+    // t = E + (O << 32)
+    t[0] = E[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;\n\t"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+          "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
+          "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]),
+          "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+#else
+    fe_mul_wide_c(t, a, b);
+#endif
+}
+
+AFC_HD void fe_mul(fe& h, const fe& f, const fe& g) {
+    uint32_t t[16];
+    fe_mul_wide(t, f.v, g.v);
+    fe_fold16(h, t);
+}
+
+// t[0..15] = a^2
+AFC_HD void fe_sq_wide(uint32_t* t, const uint32_t* a) {
+#if defined(AFC_FE_SQ_AS_MUL)
+    fe_mul_wide(t, a, a);
+#else
+    fe_sq_wide_c(t, a);     // 36 IMAD.WIDE via the compiler (vs 64 for the general product)
+#endif
+}
+
+AFC_HD void fe_sq(fe& h, const fe& f) {
+    uint32_t t[16];
+    fe_sq_wide(t, f.v);
+    fe_fold16(h, t);
+}
+
+AFC_HD void fe_sqn(fe& h, const fe& f, int n) {
+    fe_sq(h, f);
+    for (int i = 1; i < n; i++) fe_sq(h, h);
+}
+
+// ---------------------------------------------------------------------------------- encode / decode
+// Go field.Element.SetBytes: bit 255 ignored, values >= p accepted (no canonical check).
+AFC_HD void fe_frombytes_words(fe& h, const uint32_t* le_words) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = le_words[i];
+    h.v[7] &= 0x7fffffffu;
+}
+
+// canonical little-endian words of f mod p
+AFC_HD void fe_towords(uint32_t* out, const fe& f) {
+    uint32_t r[8];
+    uint64_t c;
+    // fold bit 255: x = (x mod 2^255) + 19*(x >> 255)   -> x < 2^255 + 19
+    c = (uint64_t)(f.v[7] >> 31) * 19u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (i == 7) ? (f.v[7] & 0x7fffffffu) : f.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+    // y = x + 19; if y >= 2^255 then x >= p and x - p = y - 2^255
+    uint32_t y[8];
+    c = 19;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += r[i]; y[i] = (uint32_t)c; c >>= 32; }
+    uint32_t ge = y[7] >> 31;           // 1 iff x >= p
+    uint32_t m = 0u - ge;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = (r[i] & ~m) | (y[i] & m);
+    out[7] &= 0x7fffffffu;
+}
+AFC_HD int fe_isnegative(const fe& f) { uint32_t w[8]; fe_towords(w, f); return (int)(w[0] & 1u); }
+AFC_HD int fe_iszero(const fe& f) {
+    uint32_t w[8]; fe_towords(w, f);
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= w[i];
+    return o == 0;
+}
+AFC_HD int fe_equal(const fe& a, const fe& b) { fe d; fe_sub(d, a, b); return fe_iszero(d); }
+
+// ---------------------------------------------------------------------------------- exponentiations
+// z^(2^250-1) and z^11 (shared prefix of the inversion and square-root chains)
+AFC_HD void fe_pow_2_250_m1(fe& out, fe& z11, const fe& z) {
+    fe t0, t1, t2, t3;
+    fe_sq(t0, z);                               // 2
+    fe_sqn(t1, t0, 2);                          // 8
+    fe_mul(t1, z, t1);                          // 9
+    fe_mul(t0, t0, t1);                         // 11
+    fe_copy(z11, t0);
+    fe_sq(t2, t0);                              // 22
+    fe_mul(t1, t1, t2);                         // 2^5-1
+    fe_sqn(t2, t1, 5);   fe_mul(t1, t2, t1);    // 2^10-1
+    fe_sqn(t2, t1, 10);  fe_mul(t2, t2, t1);    // 2^20-1
+    fe_sqn(t3, t2, 20);  fe_mul(t2, t3, t2);    // 2^40-1
+    fe_sqn(t2, t2, 10);  fe_mul(t1, t2, t1);    // 2^50-1
+    fe_sqn(t2, t1, 50);  fe_mul(t2, t2, t1);    // 2^100-1
+    fe_sqn(t3, t2, 100); fe_mul(t2, t3, t2);    // 2^200-1
+    fe_sqn(t2, t2, 50);  fe_mul(out, t2, t1);   // 2^250-1
+}
+AFC_HD void fe_invert(fe& out, const fe& z) {
+    fe t, z11;
+    fe_pow_2_250_m1(t, z11, z);
+    fe_sqn(t, t, 5);
+    fe_mul(out, t, z11);                        // z^(2^255-21) = z^(p-2)
+}
+AFC_HD void fe_pow22523(fe& out, const fe& z) {
+    fe t, z11;
+    fe_pow_2_250_m1(t, z11, z);
+    fe_sqn(t, t, 2);
+    fe_mul(out, t, z);                          // z^(2^252-3) = z^((p-5)/8)
+}
+
+}  // namespace afc

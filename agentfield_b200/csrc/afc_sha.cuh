@@ -1,0 +1,233 @@
+// SHA-256 / SHA-512 / HMAC-SHA256 per-message device routines (FIPS 180-4, RFC 2104).
+//
+// Replaces, per message, what the reference reaches through Go's crypto/sha256, crypto/sha512 and
+// crypto/hmac:  vc_service.go:513 (hashData), did_service.go:517 (derivePrivateKey),
+// payload_store.go:69 (payload digest), webhook_dispatcher.go:470-474 (generateWebhookSignature), and
+// the SHA-512 passes inside ed25519.Sign / ed25519.Verify (vc_service.go:463,504).
+//
+// sm_100a notes: 32-bit rotates are single funnel shifts (SHF.R.W), Ch/Maj/xor3 are single LOP3s; the
+// round constants live in __constant__ memory and, with the rounds fully unrolled, become immediate
+// constant-bank operands (c[bank][off]) — no load instructions, no shared-memory traffic.
+#pragma once
+#include "afc_common.cuh"
+
+#if !defined(AFC_HOSTSIM)
+#define AFC_CONST_DECL static __device__ __constant__
+#endif
+#include "afc_consts.inc"
+
+namespace afc {
+
+// ---------------------------------------------------------------------------------- SHA-256
+AFC_HD uint32_t ch32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (~x & z); }
+AFC_HD uint32_t maj32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (x & z) ^ (y & z); }
+
+// One compression: st += F(st, w[0..15]) — w is consumed (used as the rolling schedule window).
+AFC_HD void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        }
+        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[i] + w[i & 15];
+        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+AFC_HD void sha256_init(uint32_t st[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = AFC_H256[i];
+}
+
+// Absorb `len` message bytes after `prior` bytes have already been compressed into st (prior % 64 == 0),
+// then pad and finish.  st holds the digest words (big-endian order) on return.
+AFC_HD void sha256_finish_stream(uint32_t st[8], const uint8_t* msg, uint64_t len, uint64_t prior) {
+    PadStream ps; ps.init(msg, len);
+    uint64_t total = prior + len;
+    uint64_t nblk = (len + 9 + 63) / 64;
+    for (uint64_t blk = 0; blk < nblk; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = ps.next_be();
+        if (blk == nblk - 1) { w[14] = (uint32_t)((total * 8) >> 32); w[15] = (uint32_t)(total * 8); }
+        sha256_compress(st, w);
+    }
+}
+
+AFC_HD void sha256_msg(uint32_t st[8], const uint8_t* msg, uint64_t len) {
+    sha256_init(st);
+    sha256_finish_stream(st, msg, len, 0);
+}
+
+// SHA-256 of a short in-register message of nwords*4 bytes (nwords <= 13 -> single block).
+template <int NWORDS>
+AFC_HD void sha256_words(uint32_t st[8], const uint32_t* be_words) {
+    static_assert(NWORDS <= 13, "single block only");
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = (i < NWORDS) ? be_words[i] : 0u;
+    w[NWORDS] = 0x80000000u;
+    w[15] = NWORDS * 32;
+    sha256_init(st);
+    sha256_compress(st, w);
+}
+
+// RFC 6962 interior node: SHA-256(0x01 || left || right), 65 bytes -> 2 blocks.  l, r: big-endian words.
+AFC_HD void sha256_merkle_node(uint32_t out[8], const uint32_t l[8], const uint32_t r[8]) {
+    uint32_t w[16];
+    w[0] = 0x01000000u | (l[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[i] = (l[i - 1] << 24) | (l[i] >> 8);
+    w[8] = (l[7] << 24) | (r[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[8 + i] = (r[i - 1] << 24) | (r[i] >> 8);
+    sha256_init(out);
+    sha256_compress(out, w);
+    w[0] = (r[7] << 24) | 0x00800000u;
+#pragma unroll
+    for (int i = 1; i < 15; i++) w[i] = 0;
+    w[15] = 65 * 8;
+    sha256_compress(out, w);
+}
+
+// RFC 6962 leaf: SHA-256(0x00 || leaf).  One prefix byte, then the message stream — handled by
+// feeding the stream shifted by one byte.
+AFC_HD void sha256_merkle_leaf(uint32_t st[8], const uint8_t* leaf, uint64_t len) {
+    PadStream ps; ps.init(leaf, len);
+    uint64_t total = len + 1;
+    uint64_t nblk = (total + 9 + 63) / 64;
+    uint32_t carry = 0;                 // the 0x00 domain-separation byte, in the top 8 bits position
+    sha256_init(st);
+    for (uint64_t blk = 0; blk < nblk; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t x = ps.next_be();
+            w[i] = (carry << 24) | (x >> 8);
+            carry = x & 0xffu;
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)((total * 8) >> 32); w[15] = (uint32_t)(total * 8); }
+        sha256_compress(st, w);
+    }
+}
+
+// HMAC-SHA256 (RFC 2104) exactly as Go's hmac.New(sha256.New, key): keys longer than the 64-byte block
+// are hashed first; shorter keys are zero-padded.
+AFC_HD void hmac_sha256_msg(uint32_t out[8], const uint8_t* key, uint32_t klen, const uint8_t* msg, uint64_t len) {
+    uint32_t k0[16];
+    if (klen > 64) {
+        uint32_t kd[8];
+        sha256_msg(kd, key, klen);
+#pragma unroll
+        for (int i = 0; i < 16; i++) k0[i] = (i < 8) ? kd[i] : 0u;
+    } else {
+        MsgReader rd; rd.init(key, klen);
+        uint32_t rem = klen;            // zero padding only: no 0x80 marker
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t w = 0;
+            if (rem >= 4) { w = rd.next(); rem -= 4; }
+            else if (rem) { w = rd.next() & ((1u << (8 * rem)) - 1u); rem = 0; }
+            k0[i] = bswap32(w);
+        }
+    }
+    uint32_t st[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = k0[i] ^ 0x36363636u;
+    sha256_init(st);
+    sha256_compress(st, w);
+    sha256_finish_stream(st, msg, len, 64);
+    // outer: H(opad-block || inner digest)
+    uint32_t inner[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) inner[i] = st[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = k0[i] ^ 0x5c5c5c5cu;
+    sha256_init(out);
+    sha256_compress(out, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = inner[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 32) * 8;
+    sha256_compress(out, w);
+}
+
+AFC_HD void store_digest256(uint8_t* out, const uint32_t st[8]) {
+#if AFC_DEVICE_CODE
+    if ((((uintptr_t)out) & 15) == 0) {
+        uint4 a = make_uint4(bswap32(st[0]), bswap32(st[1]), bswap32(st[2]), bswap32(st[3]));
+        uint4 b = make_uint4(bswap32(st[4]), bswap32(st[5]), bswap32(st[6]), bswap32(st[7]));
+        ((uint4*)out)[0] = a; ((uint4*)out)[1] = b;
+        return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < 8; i++) store_be32(out + 4 * i, st[i]);
+}
+
+// ---------------------------------------------------------------------------------- SHA-512
+AFC_HD void sha512_compress(uint64_t st[8], uint64_t w[16]) {
+    uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 80; i++) {
+        if (i >= 16) {
+            uint64_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            uint64_t s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+            uint64_t s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        }
+        uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + AFC_K512[i] + w[i & 15];
+        uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// SHA-512( prefix (PW 32-bit words, given as LITTLE-endian-loaded words of the byte string) || msg ).
+// PW must be even and <= 24.  Digest returned as 64 bytes little-endian-loaded into 16 u32 (i.e. the
+// digest byte string viewed as LE words — the form the scalar reduction wants).
+template <int PW>
+AFC_HD void sha512_prefixed(uint32_t digest_le[16], const uint32_t* prefix_le, const uint8_t* msg, uint64_t len) {
+    static_assert(PW % 2 == 0 && PW <= 24, "prefix must be whole 64-bit words and leave room in block 0");
+    uint64_t st[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = AFC_H512[i];
+    PadStream ps; ps.init(msg, len);
+    uint64_t total = (uint64_t)PW * 4 + len;
+    uint64_t nblk = (total + 17 + 127) / 128;
+    for (uint64_t blk = 0; blk < nblk; blk++) {
+        uint64_t w[16];
+        if (blk == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t hi, lo;
+                if (2 * i < PW) { hi = bswap32(prefix_le[2 * i]); lo = bswap32(prefix_le[2 * i + 1]); }
+                else { hi = ps.next_be(); lo = ps.next_be(); }
+                w[i] = ((uint64_t)hi << 32) | lo;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t hi = ps.next_be(), lo = ps.next_be();
+                w[i] = ((uint64_t)hi << 32) | lo;
+            }
+        }
+        if (blk == nblk - 1) { w[14] = 0; w[15] = total * 8; }
+        sha512_compress(st, w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        digest_le[2 * i] = bswap32((uint32_t)(st[i] >> 32));
+        digest_le[2 * i + 1] = bswap32((uint32_t)st[i]);
+    }
+}
+
+}  // namespace afc

@@ -1,0 +1,152 @@
+/* afcrypto.h — C ABI of libafcrypto.so: the B200 (sm_100a) drop-in for AgentField's cryptographic
+ * identity-and-audit hot path.  Plain pointers and sizes only; no CUDA or torch types in signatures
+ * (streams are passed as void*).  This is exactly what the reference-side cgo adapter binds
+ * (INTEGRATION.md shows the Go stubs); each entry point cites the reference code it replaces, relative
+ * to /root/reference/control-plane.
+ *
+ * Conventions
+ *   - Batches are PACKED: one contiguous byte buffer + an offsets array of n+1 uint64 (msg i is
+ *     bytes [off[i], off[i+1])).  No pointer-to-pointer (cgo cannot pass [][]byte without copying).
+ *   - The caller owns every buffer; nothing is retained past return.
+ *   - Return 0 on success, negative AFC_E* on failure.  An INVALID SIGNATURE IS NOT AN ERROR: it is
+ *     ok[i] = 0 (mirrors how the reference turns failures into Valid:false, vc_service.go:242-289).
+ *   - There is NO CPU implementation behind these calls: without a usable CUDA device afc_init fails
+ *     with AFC_ECUDA and every other call fails with AFC_EINVAL (NULL ctx).  The reference-side adapter
+ *     keeps Go's stdlib as ITS fallback, not this library.
+ *   - Thread-safe and re-entrant: each call takes a stream + staging slot from the ctx pool.
+ *   - "_dev" variants take DEVICE pointers and a cudaStream_t (as void*); they only enqueue work.
+ */
+#ifndef AFCRYPTO_H
+#define AFCRYPTO_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFC_OK 0
+#define AFC_EINVAL (-1) /* bad argument / bad length (e.g. Go would panic on len(pk) != 32) */
+#define AFC_ECUDA (-2)  /* CUDA runtime failure or no device; see afc_last_cuda_error() */
+#define AFC_ENOMEM (-3) /* host or device allocation failed */
+#define AFC_ENCCL (-4)  /* NCCL failure / NCCL not available */
+#define AFC_ESTATE (-5) /* call not valid in the current state */
+
+typedef struct afc_ctx afc_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------------------------------
+ * device: CUDA ordinal this context drives (one context per GPU; the control plane shards its pending
+ * credential queue round-robin over contexts — SURVEY.md §8e).  Builds the base-point tables on the
+ * device. */
+int afc_init(int device, afc_ctx** out);
+void afc_destroy(afc_ctx* ctx);
+const char* afc_strerror(int rc);
+const char* afc_last_cuda_error(afc_ctx* ctx);
+const char* afc_version(void);
+/* device facts for benchmarks: SM count, SM clock kHz, global memory bytes */
+int afc_device_info(afc_ctx* ctx, int* sm_count, int* clock_khz, uint64_t* mem_bytes);
+/* number of kernel launches issued through this ctx since init (bench "gpu_launches") */
+uint64_t afc_launch_count(afc_ctx* ctx);
+
+/* pinned host staging for the adapter's packing buffers (cudaHostAlloc / cudaFreeHost) */
+void* afc_alloc_pinned(size_t bytes);
+void afc_free_pinned(void* p);
+
+/* ---- H1/H2: SHA-256 -----------------------------------------------------------------------------
+ * replaces sha256.Sum256 in VCService.hashData (internal/services/vc_service.go:508-515), the
+ * streaming digest in FilePayloadStore.SaveFromReader (internal/services/payload_store.go:69-94)
+ * and the seed derivation hash (internal/services/did_service.go:515-521).  out32: n x 32 bytes. */
+int afc_sha256_batch(afc_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, uint8_t* out32);
+int afc_sha256_batch_dev(afc_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, uint32_t n,
+                         uint8_t* d_out32, void* stream);
+
+/* ---- W1: HMAC-SHA256 ----------------------------------------------------------------------------
+ * replaces generateWebhookSignature (internal/services/webhook_dispatcher.go:470-474): tag =
+ * HMAC-SHA256(key = secret bytes, msg = body); the "sha256="+hex header text stays host-side.
+ * Keys longer than 64 bytes are pre-hashed (RFC 2104, as Go's hmac.New).  key_off: n+1 uint32. */
+int afc_hmac_sha256_batch(afc_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* msgs,
+                          const uint64_t* msg_off, uint32_t n, uint8_t* out32);
+int afc_hmac_sha256_batch_dev(afc_ctx* ctx, const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_msgs,
+                              const uint64_t* d_msg_off, uint32_t n, uint8_t* d_out32, void* stream);
+
+/* ---- E2: Ed25519 verify -------------------------------------------------------------------------
+ * replaces ed25519.Verify in VCService.verifyVCSignature (internal/services/vc_service.go:469-505),
+ * verifyWorkflowVCSignature (:1589-1625) and EnhancedVCVerifier.verifyVCSignature
+ * (internal/cli/vc_verification_enhanced.go:418-454).  pks: n x 32, sigs: n x 64, ok: n x 1 (0/1).
+ * Bit-exact with Go 1.24: S must be canonical, sig[63]&0xE0 must be 0, non-canonical / small-order A
+ * accepted, cofactor-less equation, R compared byte-wise with the canonical encoding.
+ * (Go panics on len(pk) != 32: the adapter checks lengths before packing and re-panics.) */
+int afc_ed25519_verify_batch(afc_ctx* ctx, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs,
+                             const uint64_t* msg_off, uint32_t n, uint8_t* ok);
+int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_sigs, const uint8_t* d_msgs,
+                                 const uint64_t* d_msg_off, uint32_t n, uint8_t* d_ok, void* stream);
+
+/* ---- E1/K1: Ed25519 sign, public keys -----------------------------------------------------------
+ * replaces ed25519.NewKeyFromSeed + ed25519.Sign in VCService.signVC / signWorkflowVC
+ * (internal/services/vc_service.go:434-466, :686-718) and NewKeyFromSeed in
+ * DIDService.derivePrivateKey (internal/services/did_service.go:515-525).
+ * seeds: n x 32; sigs: n x 64 (R || S); pks: n x 32. */
+int afc_ed25519_sign_batch(afc_ctx* ctx, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* msg_off,
+                           uint32_t n, uint8_t* sigs);
+int afc_ed25519_sign_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, const uint8_t* d_msgs, const uint64_t* d_msg_off,
+                               uint32_t n, uint8_t* d_sigs, void* stream);
+int afc_ed25519_pubkey_batch(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* pks);
+int afc_ed25519_pubkey_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_pks, void* stream);
+/* expanded keys (the N1 identity cache): 96 bytes per key = clamped scalar s (32) || prefix (32) || pk (32).
+ * Removes the two redundant fixed-base multiplications the reference does per issued VC
+ * (did_service.go:585-599 via ResolveDID, vc_service.go:460). */
+int afc_ed25519_expand_batch(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* expanded96);
+int afc_ed25519_sign_expanded_batch(afc_ctx* ctx, const uint8_t* expanded96, const uint32_t* key_index,
+                                    uint32_t n_keys, const uint8_t* msgs, const uint64_t* msg_off, uint32_t n,
+                                    uint8_t* sigs);
+int afc_ed25519_expand_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_expanded96, void* stream);
+int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, const uint32_t* d_key_index,
+                                        const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n,
+                                        uint8_t* d_sigs, void* stream);
+
+/* ---- M1: RFC 6962 Merkle audit log (NEW — the reference's chain check is a stub,
+ * internal/cli/vc_verification_enhanced.go:531-534; nearest code generateWorkflowVCDocument,
+ * internal/services/vc_service.go:525-632) -----------------------------------------------------------
+ * leaf hash = SHA-256(0x00 || leaf), node = SHA-256(0x01 || l || r), split at the largest power of two
+ * < n.  The log state (leaf count + <= 64 frontier hashes) lives in a afc_merkle handle on the device.
+ * afc_merkle_append adds n leaves and returns the new root and size. */
+typedef struct afc_merkle afc_merkle;
+int afc_merkle_new(afc_ctx* ctx, afc_merkle** out);
+void afc_merkle_free(afc_merkle* m);
+int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf_off, uint32_t n,
+                      uint8_t root32[32], uint64_t* tree_size);
+int afc_merkle_append_dev(afc_merkle* m, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, void* stream);
+/* append n already-hashed nodes (32 bytes each) as leaves-of-this-tree: used to fold per-GPU subtree
+ * roots after the all-gather, and to resume a log from stored leaf hashes */
+int afc_merkle_append_hashes(afc_merkle* m, const uint8_t* hashes32, uint32_t n, uint8_t root32[32], uint64_t* tree_size);
+int afc_merkle_append_hashes_dev(afc_merkle* m, const uint8_t* d_hashes32, uint32_t n, void* stream);
+int afc_merkle_root(afc_merkle* m, uint8_t root32[32], uint64_t* tree_size);
+int afc_merkle_root_dev(afc_merkle* m, uint8_t* d_root32, void* stream);
+/* checkpoint / resume: frontier = up to 64 (height, hash) entries; buffer of 8 + 64*32 bytes */
+#define AFC_MERKLE_STATE_BYTES (8 + 64 * 32)
+int afc_merkle_save(afc_merkle* m, uint8_t* state);
+int afc_merkle_load(afc_merkle* m, const uint8_t* state);
+/* one-shot: leaf hashes of a batch (SHA-256(0x00 || leaf)), n x 32 */
+int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n,
+                               uint8_t* d_out32, void* stream);
+
+/* ---- multi-GPU: independent shards, one exchange step --------------------------------
+ * Each rank appends its contiguous, 2^k-aligned leaf range to its own afc_merkle; the 32-byte subtree
+ * roots are all-gathered (NCCL over NVLink) and every rank folds the top levels redundantly.
+ * NCCL is dlopen'ed lazily (libnccl.so.2); unique_id is ncclUniqueId (128 bytes). */
+int afc_comm_unique_id(uint8_t id128[128]);
+int afc_comm_init(afc_ctx* ctx, int nranks, int rank, const uint8_t id128[128]);
+int afc_comm_allgather_roots(afc_ctx* ctx, const uint8_t local_root32[32], uint8_t* all_roots /* nranks x 32 */);
+int afc_comm_destroy(afc_ctx* ctx);
+
+/* ---- diagnostics --------------------------------------------------------------------------------
+ * afc_selftest: runs the PTX field arithmetic against the portable reference ON THE DEVICE for `iters`
+ * random operands (returns number of mismatches, or negative error).
+ * afc_microbench: register-only throughput of a primitive; which = 0 fe_mul, 1 fe_sq, 2 fe_add,
+ * 3 sha256 compress, 4 sha512 compress; returns primitive-ops per second (whole GPU) in *ops_per_s. */
+int afc_selftest(afc_ctx* ctx, uint32_t iters);
+int afc_microbench(afc_ctx* ctx, int which, uint32_t iters, double* ops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFCRYPTO_H */

@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""Writes the golden fixtures under tests/golden/ (run from the repo root; no GPU needed).
+
+The reference pins nothing on this path (§8c) and the Go toolchain is absent, so
+the fixtures are (a) published known-answer vectors transcribed from RFC 8032 §7.1, RFC 4231,
+FIPS 180-4 and the RFC 6962 / Certificate-Transparency reference tree — each one RE-VERIFIED below
+against OpenSSL (`cryptography`, hashlib, hmac) before it is written, so a transcription slip cannot be
+committed — and (b) edge-case and synthetic vectors produced by the oracle restatement
+(oracle/go_ed25519.py, Go's accept/reject rules) and cross-signed by OpenSSL / libsodium where those
+libraries agree with Go.
+
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import hmac
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import go_ed25519 as G, go_hash as H, merkle as M  # noqa: E402
+
+from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey, Ed25519PublicKey  # noqa: E402
+import nacl.signing  # noqa: E402
+import nacl.exceptions  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dump(name, obj):
+    with open(os.path.join(OUT, name), "w") as f:
+        json.dump(obj, f, indent=1, sort_keys=True)
+        f.write("\n")
+
+
+def ossl_verify(pk, msg, sig):
+    try:
+        Ed25519PublicKey.from_public_bytes(pk).verify(sig, msg)
+        return True
+    except Exception:
+        return False
+
+
+def sodium_verify(pk, msg, sig):
+    try:
+        nacl.signing.VerifyKey(pk).verify(msg, sig)
+        return True
+    except Exception:
+        return False
+
+
+# ----------------------------------------------------------------------------- RFC 8032 §7.1
+RFC8032 = [
+    ("TEST 1", "9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60",
+     "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a", "",
+     "e5564300c360ac729086e2cc806e828a84877f1eb8e5d974d873e06522490155"
+     "5fb8821590a33bacc61e39701cf9b46bd25bf5f0595bbe24655141438e7a100b"),
+    ("TEST 2", "4ccd089b28ff96da9db6c346ec114e0f5b8a319f35aba624da8cf6ed4fb8a6fb",
+     "3d4017c3e843895a92b70aa74d1b7ebc9c982ccf2ec4968cc0cd55f12af4660c", "72",
+     "92a009a9f0d4cab8720e820b5f642540a2b27b5416503f8fb3762223ebdb69da"
+     "085ac1e43e15996e458f3613d0f11d8c387b2eaeb4302aeeb00d291612bb0c00"),
+    ("TEST 3", "c5aa8df43f9f837bedb7442f31dcb7b166d38535076f094b85ce3a2e0b4458f7",
+     "fc51cd8e6218a1a38da47ed00230f0580816ed13ba3303ac5deb911548908025", "af82",
+     "6291d657deec24024827e69c3abe01a30ce548a284743a445e3680d7db5ac3ac"
+     "18ff9b538d16f290ae67f760984dc6594a7c15e9716ed28dc027beceea1ec40a"),
+    ("TEST SHA(abc)", "833fe62409237b9d62ec77587520911e9a759cec1d19755b7da901b96dca3d42",
+     "ec172b93ad5e563bf4932c70e1245034c35467ef2efd4d64ebf819683467e2bf",
+     hashlib.sha512(b"abc").hexdigest(),
+     "dc2a4459e7369633a52b1bf277839a00201009a3efbf3ecb69bea2186c26b589"
+     "09351fc9ac90b3ecfdfbc7c66431e0303dca179c138ac17ad9bef1177331a704"),
+]
+
+
+def make_rfc8032():
+    out = []
+    for name, seed, pk, msg, sig in RFC8032:
+        seed_b, pk_b, msg_b, sig_b = map(bytes.fromhex, (seed, pk, msg, sig))
+        sk = Ed25519PrivateKey.from_private_bytes(seed_b)
+        assert sk.public_key().public_bytes_raw() == pk_b, name
+        assert sk.sign(msg_b) == sig_b, name          # OpenSSL reproduces the published signature
+        assert G.sign(seed_b, msg_b) == sig_b and G.verify(pk_b, msg_b, sig_b), name
+        out.append({"name": "RFC 8032 §7.1 " + name, "seed": seed, "pk": pk, "msg": msg, "sig": sig})
+    # TEST 1024 (1023-byte message) is not transcribed (too long to transcribe reliably offline); long
+    # messages are covered by OpenSSL-signed synthetic vectors instead, labelled as such.
+    rng = np.random.default_rng(0xAF8032)
+    for n in (111, 112, 127, 128, 129, 511, 512, 513, 1023, 1300, 4096):
+        seed_b = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        msg_b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        sk = Ed25519PrivateKey.from_private_bytes(seed_b)
+        sig_b = sk.sign(msg_b)
+        assert G.sign(seed_b, msg_b) == sig_b
+        out.append({"name": "synthetic len=%d (signed by OpenSSL 3, equals oracle)" % n, "seed": seed_b.hex(),
+                    "pk": sk.public_key().public_bytes_raw().hex(), "msg": msg_b.hex(), "sig": sig_b.hex()})
+    dump("rfc8032.json", out)
+
+
+# ----------------------------------------------------------------------------- FIPS 180-4
+def make_fips180():
+    known = [
+        ("sha256", b"abc", "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"),
+        ("sha256", b"", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"),
+        ("sha256", b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq",
+         "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"),
+        ("sha256", b"a" * 1000000, "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0"),
+        ("sha256", b"hello world", "b94d27b9934d3e08a52e52d7da7dabfac484efe37a5380ee9088f7ace2efcde9"),  # payload_store_test.go:29-30
+        ("sha512", b"abc", "ddaf35a193617abacc417349ae20413112e6fa4e89a97ea20a9eeee64b55d39a"
+                           "2192992a274fc1a836ba3c23a3feebbd454d4423643ce80e2a9ac94fa54ca49f"),
+        ("sha512", b"", "cf83e1357eefb8bdf1542850d66d8007d620e4050b5715dc83f4a921d36ce9ce"
+                        "47d0d13c5d85f2b0ff8318d2877eec2f63b931bd47417a81a538327af927da3e"),
+    ]
+    out = []
+    for alg, msg, dig in known:
+        assert getattr(hashlib, alg)(msg).hexdigest() == dig, (alg, msg[:8])
+        if len(msg) > 4096:
+            out.append({"alg": alg, "repeat": "61", "count": len(msg), "digest": dig, "source": "FIPS 180-4 / NIST CAVP"})
+        else:
+            out.append({"alg": alg, "msg": msg.hex(), "digest": dig, "source": "FIPS 180-4 / NIST CAVP"})
+    # padding-boundary lengths, digests by OpenSSL (hashlib)
+    rng = np.random.default_rng(0xAF180)
+    for alg, lens in (("sha256", (1, 55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 256, 512, 685, 1300)),
+                      ("sha512", (1, 111, 112, 113, 127, 128, 129, 239, 240, 255, 256, 576, 1300))):
+        for n in lens:
+            msg = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            out.append({"alg": alg, "msg": msg.hex(), "digest": getattr(hashlib, alg)(msg).hexdigest(),
+                        "source": "padding boundary len=%d, OpenSSL" % n})
+    dump("fips180.json", out)
+
+
+# ----------------------------------------------------------------------------- RFC 4231
+def make_rfc4231():
+    cases = [
+        (1, b"\x0b" * 20, b"Hi There", "b0344c61d8db38535ca8afceaf0bf12b881dc200c9833da726e9376c2e32cff7"),
+        (2, b"Jefe", b"what do ya want for nothing?", "5bdcc146bf60754e6a042426089575c75a003f089d2739839dec58b964ec3843"),
+        (3, b"\xaa" * 20, b"\xdd" * 50, "773ea91e36800e46854db8ebd09181a72959098b3ef8c122d9635514ced565fe"),
+        (4, bytes(range(1, 26)), b"\xcd" * 50, "82558a389a443c0ea4cc819899f2083a85f0faa3e578f8077a2e3ff46729665b"),
+        (5, b"\x0c" * 20, b"Test With Truncation", "a3b6167473100ee06e0c796c2955552b"),
+        (6, b"\xaa" * 131, b"Test Using Larger Than Block-Size Key - Hash Key First",
+         "60e431591ee0b67f0d8a26aacbf5b77f8e0bc6213728c5140546040f0ee37f54"),
+        (7, b"\xaa" * 131, b"This is a test using a larger than block-size key and a larger than block-size data. "
+                            b"The key needs to be hashed before being used by the HMAC algorithm.",
+         "9b09ffa71b942fcb27635fbcd5b0e944bfdc63644f0713938a7f51535c3a35e2"),
+    ]
+    out = []
+    for num, key, msg, tag in cases:
+        full = hmac.new(key, msg, hashlib.sha256).hexdigest()
+        assert full.startswith(tag), num
+        out.append({"name": "RFC 4231 case %d" % num, "key": key.hex(), "msg": msg.hex(), "tag": full,
+                    "published_prefix": tag})
+    rng = np.random.default_rng(0xAF4231)
+    for klen, mlen in ((1, 0), (32, 256), (63, 55), (64, 64), (65, 119), (100, 250), (4096, 256), (32, 1300)):
+        key = rng.integers(0, 256, klen, dtype=np.uint8).tobytes()
+        msg = rng.integers(0, 256, mlen, dtype=np.uint8).tobytes()
+        out.append({"name": "synthetic klen=%d mlen=%d (OpenSSL)" % (klen, mlen), "key": key.hex(), "msg": msg.hex(),
+                    "tag": hmac.new(key, msg, hashlib.sha256).hexdigest()})
+    # reference-shaped header (webhook_dispatcher.go:470-474)
+    body = b'{"event":"execution.completed","execution_id":"exec_1","workflow_id":"wf_1","status":"succeeded"}'
+    out.append({"name": "webhook header shape", "key": b"s3cr3t".hex(), "msg": body.hex(),
+                "tag": hmac.new(b"s3cr3t", body, hashlib.sha256).hexdigest(), "header": H.webhook_signature("s3cr3t", body)})
+    dump("rfc4231.json", out)
+
+
+# ----------------------------------------------------------------------------- RFC 6962 / CT reference tree
+def make_rfc6962():
+    leaves = ["", "00", "10", "2021", "3031", "40414243", "5051525354555657", "606162636465666768696a6b6c6d6e6f"]
+    roots = [
+        "6e340b9cffb37a989ca544e6bb780a2c78901d3fb33738768511a30617afa01d",
+        "fac54203e7cc696cf0dfcb42c92a1d9dbaf70ad9e621f4bd8d98662f00e3c125",
+        "aeb6bcfe274b70a14fb067a5e5578264db0fa9b51af5e0ba159158f329e06e77",
+        "d37ee418976dd95753c1c73862b9398fa2a2cf9b4ff0fdfe8b30cd95209614b7",
+        "4e3bbb1f7b478dcfe71fb631631519a3bca12c9aefca1612bfce4c13a86264d4",
+        "76e67dadbcdf1e10e1b74ddc608abd2f98dfb16fbce75277b5232a127f2087ef",
+        "ddb89be403809e325750d3d263cd78929c2942b7942a34b77e122c9594a74c8c",
+        "5dc9da79a70659a9ad559cb701ded9a2ab9d823aad2f4960cfe370eff4604328",
+    ]
+    lb = [bytes.fromhex(x) for x in leaves]
+    for n in range(1, 9):
+        assert M.root(lb[:n]).hex() == roots[n - 1] == M.root_recursive(lb[:n]).hex(), n
+    out = {"leaves": leaves, "roots": roots, "empty_root": hashlib.sha256(b"").hexdigest(), "synthetic": []}
+    rng = np.random.default_rng(0xAF6962)
+    for n, ln in ((1, 96), (2, 96), (3, 5), (7, 96), (33, 96), (100, 17), (1000, 96), (1025, 96)):
+        ls = [rng.integers(0, 256, ln, dtype=np.uint8).tobytes() for _ in range(n)]
+        r = M.root(ls)
+        assert r == M.root_recursive(ls)
+        out["synthetic"].append({"seed": "PCG64(0xAF6962) stream", "n": n, "leaf_len": ln,
+                                 "leaves_sha256": hashlib.sha256(b"".join(ls)).hexdigest(),
+                                 "leaves": [x.hex() for x in ls] if n <= 100 else None, "root": r.hex()})
+    dump("rfc6962.json", out)
+
+
+# ----------------------------------------------------------------------------- Ed25519 edge set (Go rules)
+def make_edge():
+    out = []
+    rng = np.random.default_rng(0xAFED6E)
+    seed = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    msg = rng.integers(0, 256, 512, dtype=np.uint8).tobytes()
+    pk = G.public_key(seed)
+    sig = G.sign(seed, msg)
+
+    def add(name, pk_, msg_, sig_, note=""):
+        exp = G.verify(pk_, msg_, sig_)
+        o, s = ossl_verify(pk_, msg_, sig_), sodium_verify(pk_, msg_, sig_)
+        out.append({"name": name, "pk": pk_.hex(), "msg": msg_.hex(), "sig": sig_.hex(), "valid": exp,
+                    "openssl": o, "libsodium": s, "note": note})
+        return exp
+
+    assert add("honest", pk, msg, sig)
+    s_int = int.from_bytes(sig[32:], "little")
+    assert not add("S = L", pk, msg, sig[:32] + int(G.L).to_bytes(32, "little"))
+    assert not add("S + L (non-canonical S, same residue)", pk, msg, sig[:32] + int(s_int + G.L).to_bytes(32, "little"),
+                   "Go SetCanonicalBytes rejects; RFC 8032 says reject")
+    hi = bytearray(sig); hi[63] |= 0x20
+    assert not add("sig[63] bit 5 set", pk, msg, bytes(hi))
+    hi = bytearray(sig); hi[63] |= 0x80
+    assert not add("sig[63] bit 7 set", pk, msg, bytes(hi))
+    assert not add("all-zero signature", pk, msg, bytes(64))
+    for label, idx in (("msg", 0), ("msg", 511)):
+        m2 = bytearray(msg); m2[idx] ^= 1
+        assert not add("flipped bit in %s[%d]" % (label, idx), pk, bytes(m2), sig)
+    for idx in (0, 31, 32, 62):
+        s2 = bytearray(sig); s2[idx] ^= 0x04
+        assert not add("flipped bit in sig[%d]" % idx, pk, msg, bytes(s2))
+    p2 = bytearray(pk); p2[3] ^= 0x10
+    add("flipped bit in pk[3]", bytes(p2), msg, sig)        # may or may not be on-curve; never valid
+    assert not out[-1]["valid"]
+    # A not on the curve
+    y = 2
+    while G.decompress(int(y).to_bytes(32, "little")) is not None:
+        y += 1
+    assert not add("A not on curve (y=%d)" % y, int(y).to_bytes(32, "little"), msg, sig)
+    # identity public key, canonical and non-canonical encodings; R = identity, S = 0 verifies under Go
+    ident = (1).to_bytes(32, "little")
+    ident_nc = int(G.P + 1).to_bytes(32, "little")            # y = p+1 = 1 mod p (non-canonical, accepted by Go)
+    ident_sign = bytearray(ident); ident_sign[31] |= 0x80       # x = 0 with sign bit set (accepted by Go)
+    sig0 = ident + bytes(32)
+    assert add("A = identity, R = identity, S = 0", ident, msg, sig0, "small-order A accepted by Go (cofactor-less check)")
+    assert add("A = non-canonical identity (y = p+1)", ident_nc, msg, sig0, "Go ignores y >= p; RFC 8032-strict decoders reject")
+    assert add("A = identity with x-sign bit set", bytes(ident_sign), msg, sig0, "Go: x = -0 = 0 accepted")
+    assert not add("R = non-canonical identity encoding", ident, msg, ident_nc + bytes(32),
+                   "R is compared byte-wise with the canonical encoding of R'")
+    assert not add("R = identity with x-sign bit set", ident, msg, bytes(ident_sign) + bytes(32))
+    # the 8 small-order points as A: search a message for which (R = torsion point, S = 0) verifies
+    tors = G.small_order_points()
+    for a_enc in tors:
+        found = 0
+        for ctr in range(400):
+            m = b"torsion-%d" % ctr
+            for r_enc in tors:
+                if G.verify(a_enc, m, r_enc + bytes(32)):
+                    add("small-order A=%s.. R=%s.. S=0 ctr=%d" % (a_enc.hex()[:8], r_enc.hex()[:8], ctr), a_enc, m, r_enc + bytes(32),
+                        "valid under Go's cofactor-less equation; libsodium rejects small-order keys")
+                    found += 1
+                    break
+            if found >= 2:
+                break
+        assert found, a_enc.hex()
+        add("small-order A=%s.. honest-looking sig" % a_enc.hex()[:8], a_enc, msg, sig)
+    # non-canonical A that is not the identity: y in [p, 2^255) means y mod p < 19
+    for yy in range(0, 19):
+        enc = int(yy + G.P).to_bytes(32, "little")
+        pt = G.decompress(enc)
+        for sgn in (0, 0x80):
+            e2 = bytearray(enc); e2[31] |= sgn
+            add("non-canonical A y=p+%d sign=%d (%s)" % (yy, sgn >> 7, "on curve" if pt else "off curve"), bytes(e2), msg, sig)
+    # mixed-order A = honest A + torsion point: honest signature must fail, but is decodable
+    n_valid = sum(1 for o in out if o["valid"])
+    assert n_valid >= 10
+    dump("ed25519_edge.json", out)
+
+
+# ----------------------------------------------------------------------------- reference-flow vectors
+def make_flow():
+    """Key derivation + did:key + hashData + a full VC-shaped canonical message (did_service.go:515-536,
+    vc_service.go:434-515)."""
+    rng = np.random.default_rng(0xAF01)
+    master = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    out = {"master_seed": master.hex(), "derivations": [], "hash_data": [], "vc": None}
+    for path in ("m/44'/0'", "m/44'/1237'/0'", "m/44'/1237'/0'/0'/0'", "m/44'/1237'/0'/1'/3'"):
+        seed = H.derive_seed(master, path)
+        pk = G.public_key(seed)
+        assert Ed25519PrivateKey.from_private_bytes(seed).public_key().public_bytes_raw() == pk
+        out["derivations"].append({"path": path, "seed": seed.hex(), "pk": pk.hex(), "did": H.did_key(pk)})
+    for payload in (None, b"", b"{}", b'{"a":1}', bytes(range(256))):
+        enc = H.marshal_data_or_null(payload)
+        out["hash_data"].append({"payload": None if payload is None else payload.hex(), "marshalled": enc.hex(),
+                                 "hash": H.hash_data(enc)})
+    d = out["derivations"]
+    doc = ('{"@context":["https://www.w3.org/2018/credentials/v1","https://agentfield.ai/contexts/execution/v1"],'
+           '"type":["VerifiableCredential","AgentFieldExecutionCredential"],"id":"urn:agentfield:vc:vc-1789971100759287000",'
+           '"issuer":"%s","issuanceDate":"2026-09-21T06:00:00Z","credentialSubject":{"executionId":"exec_0001",'
+           '"workflowId":"wf_0001","sessionId":"sess_0001","caller":{"did":"%s","type":"agent","agentNodeDid":"%s"},'
+           '"target":{"did":"%s","agentNodeDid":"%s","functionName":"summarise"},"execution":{"inputHash":"%s",'
+           '"outputHash":"%s","timestamp":"2026-09-21T06:00:00Z","durationMs":42,"status":"succeeded"},'
+           '"audit":{"inputDataHash":"%s","outputDataHash":"%s","metadata":{"agentfield_version":"0.1.5","vc_version":"1.0"}}},'
+           '"proof":{"type":"","created":"","verificationMethod":"","proofPurpose":"","proofValue":""}}') % (
+        d[1]["did"], d[1]["did"], d[1]["did"], d[2]["did"], d[1]["did"],
+        out["hash_data"][3]["hash"], out["hash_data"][2]["hash"], out["hash_data"][3]["hash"], out["hash_data"][2]["hash"])
+    msg = doc.encode()
+    seed = bytes.fromhex(d[1]["seed"])
+    sig = G.sign(seed, msg)
+    assert Ed25519PrivateKey.from_private_bytes(seed).sign(msg) == sig
+    out["vc"] = {"canonical": doc, "len": len(msg), "seed": d[1]["seed"], "pk": d[1]["pk"], "sig": sig.hex(),
+                 "proofValue": H.b64url_nopad(sig)}
+    dump("reference_flow.json", out)
+
+
+if __name__ == "__main__":
+    make_rfc8032()
+    make_fips180()
+    make_rfc4231()
+    make_rfc6962()
+    make_edge()
+    make_flow()
+    print("golden fixtures written to", OUT)

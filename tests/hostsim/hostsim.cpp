@@ -1,0 +1,85 @@
+// tests/hostsim — TEST-ONLY CPU build of the kernel logic.
+//
+// Compiles the very same per-credential routines the sm_100a kernels inline (agentfield_b200/csrc/*.cuh)
+// with g++ and -DAFC_HOSTSIM so the no-GPU test tier can check the arithmetic (field, scalar, group,
+// hashing, padding, Merkle node layout) against the oracle BEFORE GPU time is spent.  It exercises the
+// portable code paths only (the inline-PTX paths are checked on the device by afc_selftest).
+// It is NOT part of the product: libafcrypto.so contains no CPU implementation and nothing under
+// agentfield_b200/ loads this library.
+#define AFC_HOSTSIM 1
+#include "../../agentfield_b200/csrc/afc_ge.cuh"
+
+#include <vector>
+
+using namespace afc;
+
+static std::vector<ge_precomp> g_comb;
+static void ensure_tables() {
+    if (!g_comb.empty()) return;
+    g_comb.resize(64 * 8);
+    for (int i = 0; i < 64; i++) ge_build_comb_row(&g_comb[i * 8], i);
+}
+static void words_from_bytes(uint32_t* w, const uint8_t* b, int n) { for (int i = 0; i < n; i++) w[i] = load_le32(b + 4 * i); }
+static void bytes_from_words(uint8_t* b, const uint32_t* w, int n) { for (int i = 0; i < n; i++) store_le32(b + 4 * i, w[i]); }
+
+extern "C" {
+
+void hs_sha256(const uint8_t* msg, uint64_t len, uint8_t out[32]) { uint32_t st[8]; sha256_msg(st, msg, len); for (int i = 0; i < 8; i++) store_be32(out + 4 * i, st[i]); }
+void hs_hmac_sha256(const uint8_t* key, uint32_t klen, const uint8_t* msg, uint64_t len, uint8_t out[32]) {
+    uint32_t st[8]; hmac_sha256_msg(st, key, klen, msg, len); for (int i = 0; i < 8; i++) store_be32(out + 4 * i, st[i]);
+}
+void hs_merkle_leaf(const uint8_t* leaf, uint64_t len, uint8_t out[32]) { uint32_t st[8]; sha256_merkle_leaf(st, leaf, len); for (int i = 0; i < 8; i++) store_be32(out + 4 * i, st[i]); }
+void hs_merkle_node(const uint8_t l[32], const uint8_t r[32], uint8_t out[32]) {
+    uint32_t a[8], b[8], o[8];
+    for (int i = 0; i < 8; i++) { a[i] = bswap32(load_le32(l + 4 * i)); b[i] = bswap32(load_le32(r + 4 * i)); }
+    sha256_merkle_node(o, a, b);
+    for (int i = 0; i < 8; i++) store_be32(out + 4 * i, o[i]);
+}
+// SHA-512(prefix16words || msg) digest (64 bytes) — the H(R||A||M) shape
+void hs_sha512_pre64(const uint8_t prefix[64], const uint8_t* msg, uint64_t len, uint8_t out[64]) {
+    uint32_t pre[16], dig[16]; words_from_bytes(pre, prefix, 16);
+    sha512_prefixed<16>(dig, pre, msg, len); bytes_from_words(out, dig, 16);
+}
+void hs_sha512_pre32(const uint8_t prefix[32], const uint8_t* msg, uint64_t len, uint8_t out[64]) {
+    uint32_t pre[8], dig[16]; words_from_bytes(pre, prefix, 8);
+    sha512_prefixed<8>(dig, pre, msg, len); bytes_from_words(out, dig, 16);
+}
+void hs_sc_reduce512(const uint8_t in[64], uint8_t out[32]) { uint32_t x[16], r[8]; words_from_bytes(x, in, 16); sc_reduce512(r, x); bytes_from_words(out, r, 8); }
+void hs_sc_muladd(const uint8_t a[32], const uint8_t b[32], const uint8_t c[32], uint8_t out[32]) {
+    uint32_t A[8], B[8], C[8], r[8]; words_from_bytes(A, a, 8); words_from_bytes(B, b, 8); words_from_bytes(C, c, 8);
+    sc_muladd(r, A, B, C); bytes_from_words(out, r, 8);
+}
+// field ops on raw 256-bit little-endian values; op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 canonical
+void hs_fe_op(int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+    fe x, y, r; words_from_bytes(x.v, a, 8); words_from_bytes(y.v, b, 8);
+    switch (op) {
+    case 0: fe_mul(r, x, y); break;
+    case 1: fe_sq(r, x); break;
+    case 2: fe_add(r, x, y); break;
+    case 3: fe_sub(r, x, y); break;
+    case 4: fe_invert(r, x); break;
+    default: r = x; break;
+    }
+    uint32_t w[8]; fe_towords(w, r); bytes_from_words(out, w, 8);
+}
+int hs_verify(const uint8_t pk[32], const uint8_t* msg, uint64_t len, const uint8_t sig[64]) {
+    ensure_tables();
+    uint32_t p[8], s[16], k[8];
+    words_from_bytes(p, pk, 8); words_from_bytes(s, sig, 16);
+    ed25519_hram(k, p, s, msg, len);
+    return ed25519_verify_core(p, s, k, &g_comb[0]);
+}
+void hs_pubkey(const uint8_t seed[32], uint8_t pk[32]) {
+    ensure_tables();
+    uint32_t sd[8], s[8], pre[8], p[8]; words_from_bytes(sd, seed, 8);
+    ed25519_expand(s, pre, p, sd, &g_comb[0]); bytes_from_words(pk, p, 8);
+}
+void hs_sign(const uint8_t seed[32], const uint8_t* msg, uint64_t len, uint8_t sig[64]) {
+    ensure_tables();
+    uint32_t sd[8], s[8], pre[8], p[8], sg[16]; words_from_bytes(sd, seed, 8);
+    ed25519_expand(s, pre, p, sd, &g_comb[0]);
+    ed25519_sign_expanded(sg, s, pre, p, msg, len, &g_comb[0]);
+    bytes_from_words(sig, sg, 16);
+}
+
+}  // extern "C"
