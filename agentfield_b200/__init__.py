@@ -1,0 +1,16 @@
+"""agentfield_b200 — B200-native (sm_100a) drop-in for AgentField's cryptographic identity-and-audit hot
+path: batched Ed25519 sign/verify for Verifiable Credentials, HMAC-SHA256 webhook signing, SHA-256
+payload hashing and an RFC 6962 Merkle audit log, behind the C ABI in include/afcrypto.h.
+
+Only what the path needs lives here: csrc/ (CUDA kernels + C ABI), _abi.py (ctypes binding), crypto.py /
+audit.py / identity.py / services.py (host-side mirrors of the reference's Go seams).  All arithmetic
+runs in libafcrypto.so on the GPU; there is no CPU fallback in this package.
+"""
+from . import _abi
+from ._abi import AfcError, LIB_PATH
+from .crypto import Context, Hasher, MAC, Signer, Verifier, default_context, pack, pack32
+from .audit import Auditor, fold_roots
+
+__all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "fold_roots",
+           "default_context", "pack", "pack32"]
+__version__ = "0.1.0"

@@ -1,0 +1,99 @@
+"""Host-side mirror of the Go `internal/audit` interface this build adds:
+
+    type Auditor interface{ Append(leaves [][]byte) (root [32]byte, size uint64, err error); Root() ... }
+
+A tamper-evident RFC 6962 Merkle log over issued credentials.  The reference has no such structure —
+its chain check is a stub (internal/cli/vc_verification_enhanced.go:531-534) and the workflow roll-up
+signs a list of VC *IDs* (internal/services/vc_service.go:525-632) — so the format is specified here:
+leaf = the stored vc_document bytes (or any caller-chosen record), leaf hash = SHA-256(0x00 || leaf),
+node = SHA-256(0x01 || l || r), split at the largest power of two < n.
+
+Multi-GPU: rank g appends the contiguous, 2^k-aligned leaf range it owns; the 32-byte
+subtree roots are all-gathered (NCCL over NVLink — through torch.distributed here, or the library's own
+afc_comm_* for the Go host) and every rank folds the top levels redundantly with `fold_roots`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .crypto import default_context, pack
+
+
+class Auditor:
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._lib = _abi.load()
+        h = C.c_void_p()
+        _abi.check(self._lib.afc_merkle_new(self.ctx.handle, C.byref(h)), self.ctx.handle)
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.afc_merkle_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def append(self, leaves):
+        """Append(leaves) -> (root, size)."""
+        buf, off = pack(leaves)
+        return self.append_packed(buf, off)
+
+    def append_packed(self, buf, off):
+        root = np.zeros(32, dtype=np.uint8)
+        size = C.c_uint64()
+        _abi.check(self._lib.afc_merkle_append(self.handle, _abi.ptr(buf), _abi.ptr(off), len(off) - 1, _abi.ptr(root), C.byref(size)),
+                   self.ctx.handle)
+        return root.tobytes(), size.value
+
+    def append_hashes(self, hashes):
+        """Append already-hashed nodes (n x 32) as leaves of this tree."""
+        hs = np.ascontiguousarray(hashes, dtype=np.uint8).reshape(-1, 32)
+        root = np.zeros(32, dtype=np.uint8)
+        size = C.c_uint64()
+        _abi.check(self._lib.afc_merkle_append_hashes(self.handle, _abi.ptr(hs), hs.shape[0], _abi.ptr(root), C.byref(size)), self.ctx.handle)
+        return root.tobytes(), size.value
+
+    def root(self):
+        root = np.zeros(32, dtype=np.uint8)
+        size = C.c_uint64()
+        _abi.check(self._lib.afc_merkle_root(self.handle, _abi.ptr(root), C.byref(size)), self.ctx.handle)
+        return root.tobytes(), size.value
+
+    # device-resident variants (torch tensors on the ctx's GPU)
+    def append_dev(self, d_leaves, d_off, n, stream=None):
+        _abi.check(self._lib.afc_merkle_append_dev(self.handle, _abi.ptr(d_leaves), _abi.ptr(d_off), n, self.ctx._stream(stream)), self.ctx.handle)
+
+    def append_hashes_dev(self, d_hashes, n, stream=None):
+        _abi.check(self._lib.afc_merkle_append_hashes_dev(self.handle, _abi.ptr(d_hashes), n, self.ctx._stream(stream)), self.ctx.handle)
+
+    def root_dev(self, d_root32, stream=None):
+        _abi.check(self._lib.afc_merkle_root_dev(self.handle, _abi.ptr(d_root32), self.ctx._stream(stream)), self.ctx.handle)
+
+    # checkpoint / resume: leaf count + frontier hashes
+    def save(self):
+        st = np.zeros(_abi.MERKLE_STATE_BYTES, dtype=np.uint8)
+        _abi.check(self._lib.afc_merkle_save(self.handle, _abi.ptr(st)), self.ctx.handle)
+        return st.tobytes()
+
+    def load(self, state):
+        st = np.frombuffer(state, dtype=np.uint8).copy()
+        if st.size != _abi.MERKLE_STATE_BYTES:
+            raise ValueError("bad Merkle state length")
+        _abi.check(self._lib.afc_merkle_load(self.handle, _abi.ptr(st)), self.ctx.handle)
+
+
+def fold_roots(subtree_roots, ctx=None):
+    """Root of the tree whose consecutive, equally sized 2^k-leaf blocks have the given roots (the
+    last block may be a partial block's own MTH): MTH over the block roots taken as nodes."""
+    a = Auditor(ctx)
+    try:
+        root, _ = a.append_hashes(subtree_roots)
+        return root
+    finally:
+        a.close()

@@ -353,12 +353,116 @@ AFC_HD void fe_mul(fe& h, const fe& f, const fe& g) {
     fe_fold16(h, t);
 }
 
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+// Carry-chain primitives as single instructions.  `volatile` keeps their relative order; the carry flag
+// lives in PTX's CC register, which only these instructions touch (the compiler never emits .cc forms).
+#define AFC_MAD_LO_CC(acc, x, y)   asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(y))
+#define AFC_MADC_LO_CC(acc, x, y)  asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(y))
+#define AFC_MADC_HI_CC(acc, x, y)  asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(y))
+#define AFC_MADC_HI_NEW(acc, x, y) asm volatile("madc.hi.u32 %0, %1, %2, 0;" : "=r"(acc) : "r"(x), "r"(y))
+#define AFC_MADC_LO_NEW_CC(acc, x, y) asm volatile("madc.lo.cc.u32 %0, %1, %2, 0;" : "=r"(acc) : "r"(x), "r"(y))
+#define AFC_ADDC_NEW(acc)          asm volatile("addc.u32 %0, 0, 0;" : "=r"(acc))
+#define AFC_MUL_WIDE(lo, hi, x, y) asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
+#endif
+
 // t[0..15] = a^2
 AFC_HD void fe_sq_wide(uint32_t* t, const uint32_t* a) {
 #if defined(AFC_FE_SQ_AS_MUL)
     fe_mul_wide(t, a, a);
+#elif AFC_DEVICE_CODE && AFC_FE_PTX
+    // S = sum_{i<j} a_i a_j 2^(32(i+j)) with even columns in E[k] (limb k) and odd columns in O[k] (limb k+1)
+    uint32_t E[14], O[14];
+    // row 0
+    AFC_MUL_WIDE(O[0], O[1], a[0], a[1]); AFC_MUL_WIDE(O[2], O[3], a[0], a[3]);
+    AFC_MUL_WIDE(O[4], O[5], a[0], a[5]); AFC_MUL_WIDE(O[6], O[7], a[0], a[7]);
+    AFC_MUL_WIDE(E[2], E[3], a[0], a[2]); AFC_MUL_WIDE(E[4], E[5], a[0], a[4]); AFC_MUL_WIDE(E[6], E[7], a[0], a[6]);
+    // row 1: O (2,3)(4,5)(6,7) += a1*{a2,a4,a6}, carry -> O[8];  E (4,5)(6,7) += a1*{a3,a5}, (8,9) fresh a1*a7
+    AFC_MAD_LO_CC(O[2], a[1], a[2]); AFC_MADC_HI_CC(O[3], a[1], a[2]);
+    AFC_MADC_LO_CC(O[4], a[1], a[4]); AFC_MADC_HI_CC(O[5], a[1], a[4]);
+    AFC_MADC_LO_CC(O[6], a[1], a[6]); AFC_MADC_HI_CC(O[7], a[1], a[6]);
+    AFC_ADDC_NEW(O[8]);
+    AFC_MAD_LO_CC(E[4], a[1], a[3]); AFC_MADC_HI_CC(E[5], a[1], a[3]);
+    AFC_MADC_LO_CC(E[6], a[1], a[5]); AFC_MADC_HI_CC(E[7], a[1], a[5]);
+    AFC_MADC_LO_NEW_CC(E[8], a[1], a[7]); AFC_MADC_HI_NEW(E[9], a[1], a[7]);
+    // row 2: O (4,5)(6,7) += a2*{a3,a5}, (8,9): O[8] += lo, O[9] fresh;  E (6,7)(8,9) += a2*{a4,a6}, carry -> E[10]
+    AFC_MAD_LO_CC(O[4], a[2], a[3]); AFC_MADC_HI_CC(O[5], a[2], a[3]);
+    AFC_MADC_LO_CC(O[6], a[2], a[5]); AFC_MADC_HI_CC(O[7], a[2], a[5]);
+    AFC_MADC_LO_CC(O[8], a[2], a[7]); AFC_MADC_HI_NEW(O[9], a[2], a[7]);
+    AFC_MAD_LO_CC(E[6], a[2], a[4]); AFC_MADC_HI_CC(E[7], a[2], a[4]);
+    AFC_MADC_LO_CC(E[8], a[2], a[6]); AFC_MADC_HI_CC(E[9], a[2], a[6]);
+    AFC_ADDC_NEW(E[10]);
+    // row 3: O (6,7)(8,9) += a3*{a4,a6}, carry -> O[10];  E (8,9) += a3*a5, (10,11): E[10] += lo, E[11] fresh
+    AFC_MAD_LO_CC(O[6], a[3], a[4]); AFC_MADC_HI_CC(O[7], a[3], a[4]);
+    AFC_MADC_LO_CC(O[8], a[3], a[6]); AFC_MADC_HI_CC(O[9], a[3], a[6]);
+    AFC_ADDC_NEW(O[10]);
+    AFC_MAD_LO_CC(E[8], a[3], a[5]); AFC_MADC_HI_CC(E[9], a[3], a[5]);
+    AFC_MADC_LO_CC(E[10], a[3], a[7]); AFC_MADC_HI_NEW(E[11], a[3], a[7]);
+    // row 4: O (8,9) += a4*a5, (10,11): O[10] += lo, O[11] fresh;  E (10,11) += a4*a6, carry -> E[12]
+    AFC_MAD_LO_CC(O[8], a[4], a[5]); AFC_MADC_HI_CC(O[9], a[4], a[5]);
+    AFC_MADC_LO_CC(O[10], a[4], a[7]); AFC_MADC_HI_NEW(O[11], a[4], a[7]);
+    AFC_MAD_LO_CC(E[10], a[4], a[6]); AFC_MADC_HI_CC(E[11], a[4], a[6]);
+    AFC_ADDC_NEW(E[12]);
+    // row 5: O (10,11) += a5*a6, carry -> O[12];  E (12,13): E[12] += lo, E[13] fresh
+    AFC_MAD_LO_CC(O[10], a[5], a[6]); AFC_MADC_HI_CC(O[11], a[5], a[6]);
+    AFC_ADDC_NEW(O[12]);
+    AFC_MAD_LO_CC(E[12], a[5], a[7]); AFC_MADC_HI_NEW(E[13], a[5], a[7]);
+    // row 6: O (12,13): O[12] += lo, O[13] fresh
+    AFC_MAD_LO_CC(O[12], a[6], a[7]); AFC_MADC_HI_NEW(O[13], a[6], a[7]);
+    // S = E + (O << 32): limbs 1..15 (E[0] = E[1] = 0)
+    uint32_t S1 = O[0], S2, S3, S4, S5, S6, S7, S8, S9, S10, S11, S12, S13, S14, S15;
+    asm("add.cc.u32 %0, %14, %26;\n\t"
+        "addc.cc.u32 %1, %15, %27;\n\t"
+        "addc.cc.u32 %2, %16, %28;\n\t"
+        "addc.cc.u32 %3, %17, %29;\n\t"
+        "addc.cc.u32 %4, %18, %30;\n\t"
+        "addc.cc.u32 %5, %19, %31;\n\t"
+        "addc.cc.u32 %6, %20, %32;\n\t"
+        "addc.cc.u32 %7, %21, %33;\n\t"
+        "addc.cc.u32 %8, %22, %34;\n\t"
+        "addc.cc.u32 %9, %23, %35;\n\t"
+        "addc.cc.u32 %10, %24, %36;\n\t"
+        "addc.cc.u32 %11, %25, %37;\n\t"
+        "addc.cc.u32 %12, %38, 0;\n\t"
+        "addc.u32 %13, 0, 0;\n\t"
+        : "=r"(S2), "=r"(S3), "=r"(S4), "=r"(S5), "=r"(S6), "=r"(S7), "=r"(S8), "=r"(S9), "=r"(S10), "=r"(S11),
+          "=r"(S12), "=r"(S13), "=r"(S14), "=r"(S15)
+        : "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]),
+          "r"(E[12]), "r"(E[13]),
+          "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
+          "r"(O[11]), "r"(O[12]), "r"(O[13]));
+    // T = 2S (funnel shifts, no carries) + diagonal squares
+    uint32_t D[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) AFC_MUL_WIDE(D[2 * i], D[2 * i + 1], a[i], a[i]);
+    uint32_t T1 = S1 << 1, T2 = __funnelshift_l(S1, S2, 1), T3 = __funnelshift_l(S2, S3, 1), T4 = __funnelshift_l(S3, S4, 1),
+             T5 = __funnelshift_l(S4, S5, 1), T6 = __funnelshift_l(S5, S6, 1), T7 = __funnelshift_l(S6, S7, 1),
+             T8 = __funnelshift_l(S7, S8, 1), T9 = __funnelshift_l(S8, S9, 1), T10 = __funnelshift_l(S9, S10, 1),
+             T11 = __funnelshift_l(S10, S11, 1), T12 = __funnelshift_l(S11, S12, 1), T13 = __funnelshift_l(S12, S13, 1),
+             T14 = __funnelshift_l(S13, S14, 1), T15 = __funnelshift_l(S14, S15, 1);
+    t[0] = D[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;\n\t"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+          "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "r"(D[1]), "r"(D[2]), "r"(D[3]), "r"(D[4]), "r"(D[5]), "r"(D[6]), "r"(D[7]), "r"(D[8]),
+          "r"(D[9]), "r"(D[10]), "r"(D[11]), "r"(D[12]), "r"(D[13]), "r"(D[14]), "r"(D[15]),
+          "r"(T1), "r"(T2), "r"(T3), "r"(T4), "r"(T5), "r"(T6), "r"(T7), "r"(T8),
+          "r"(T9), "r"(T10), "r"(T11), "r"(T12), "r"(T13), "r"(T14), "r"(T15));
 #else
-    fe_sq_wide_c(t, a);     // 36 IMAD.WIDE via the compiler (vs 64 for the general product)
+    fe_sq_wide_c(t, a);
 #endif
 }
 

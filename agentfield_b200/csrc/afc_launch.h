@@ -1,0 +1,69 @@
+// Internal launch API between the C-ABI layer (afcrypto.cu) and the kernel translation units
+// (k_hash.cu, k_ed25519.cu).  All pointers are DEVICE pointers; every function only enqueues work on
+// `s` and returns cudaGetLastError().  Each launch is counted (and optionally timed) through the LaunchLog.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace afc {
+namespace launch {
+
+// Launch accounting + optional per-kernel CUDA-event timing (afc_profile_*): when `profile` is set every kernel
+// launch is bracketed by two events on its own stream; afcrypto.cu aggregates them by kernel name after a sync.
+struct LaunchRec { const char* name; cudaEvent_t e0, e1; };
+struct LaunchLog {
+    unsigned long long n = 0;
+    bool profile = false;
+    LaunchRec* recs = nullptr;       // capacity `cap`, filled up to `used`
+    int cap = 0, used = 0;
+    cudaEvent_t begin(const char* name, cudaStream_t s) {
+        ++n;
+        if (!profile || used >= cap) return nullptr;
+        LaunchRec& r = recs[used];
+        r.name = name;
+        cudaEventRecord(r.e0, s);
+        return r.e1;
+    }
+    void end(cudaEvent_t e1, cudaStream_t s) { if (e1) { cudaEventRecord(e1, s); ++used; } }
+};
+#define AFC_LAUNCH(lg, name, stream, ...)            \
+    do {                                             \
+        cudaEvent_t _e1 = (lg)->begin(name, stream); \
+        __VA_ARGS__;                                 \
+        (lg)->end(_e1, stream);                      \
+    } while (0)
+
+// ---- k_hash.cu
+cudaError_t sha256_batch(const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg);
+cudaError_t hmac_sha256_batch(const uint8_t* keys, const uint32_t* koff, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                              uint8_t* out32, cudaStream_t s, LaunchLog* lg);
+cudaError_t merkle_leaf_hashes(const uint8_t* leaves, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg);
+// One tree level.  in: node array whose element 0 has level-index s_idx; npairs pairs starting at element `first`
+// (first = 1 when s_idx was odd and the left orphan in[0] merges with frontier[h]); out[carry..] receives the parents.
+//   left_merge  : out[0] = H(frontier[h] || in[0])                         (then pairs go to out[1..])
+//   right_orphan: frontier[h] = in[first + 2*npairs]
+cudaError_t merkle_level(const uint8_t* in, uint8_t* out, uint64_t npairs, int left_merge, int right_orphan,
+                         uint8_t* frontier, int h, cudaStream_t s, LaunchLog* lg);
+// root from frontier (bits of `size` say which heights are present); size == 0 -> SHA-256("")
+cudaError_t merkle_root(const uint8_t* frontier, uint64_t size, uint8_t* out32, cudaStream_t s, LaunchLog* lg);
+cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg);
+
+// ---- k_ed25519.cu
+struct EdTables { void* comb; };     // 64*8 ge_precomp (row 0 = b8)
+size_t ed_tables_bytes();
+cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg);
+// scratch_k: n * 32 bytes
+cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
+                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                          uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, const uint32_t* key_index, const uint8_t* msgs,
+                                   const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
+                            cudaStream_t s, LaunchLog* lg);
+// returns number of mismatches in *d_mismatch (device uint32)
+cudaError_t ed_selftest(uint32_t iters, uint32_t* d_mismatch, cudaStream_t s, LaunchLog* lg);
+cudaError_t microbench_fe(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg);
+
+}  // namespace launch
+}  // namespace afc

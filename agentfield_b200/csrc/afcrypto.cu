@@ -1,0 +1,802 @@
+// libafcrypto.so — C-ABI layer (include/afcrypto.h) over the sm_100a kernels.
+//
+// Host-side responsibilities only: context + stream pool, pinned/device staging, chunked
+// copy/compute overlap for host-buffer calls, the RFC 6962 level schedule, optional NCCL (dlopen).
+// There is deliberately NO CPU implementation of any primitive in this library: if CUDA is missing or
+// fails, calls return AFC_ECUDA and the reference-side adapter decides what to do.
+#include "../../include/afcrypto.h"
+#include "afc_launch.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace afc;
+
+namespace {
+
+constexpr int kLanes = 4;                 // concurrent host-buffer calls per context
+constexpr uint32_t kChunkItems = 1u << 16;  // items per pipeline chunk for host-buffer calls
+constexpr size_t kChunkBytes = 48u << 20;   // and at most this many message bytes per chunk
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc((void**)&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaHostAlloc((void**)&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// One half of a lane's double buffer
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf msgs, off, a, b, k, out, koff;   // a: pks/seeds/keys  b: sigs
+    PinBuf h_in, h_out;                      // bounce buffers when the caller's memory is not pinned
+};
+struct Lane {
+    Slot slot[2];
+    bool busy = false;
+};
+
+}  // namespace
+
+struct afc_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    void* comb = nullptr;
+    Lane lanes[kLanes];
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<unsigned long long> launches{0};
+    std::string last_error;
+    // per-kernel CUDA-event profiling (afc_profile_begin / afc_profile_end)
+    bool profile = false;
+    std::vector<launch::LaunchRec> prof_recs;
+    std::atomic<int> prof_next{0};
+    std::vector<std::pair<int, int>> prof_spans;    // (base, used) per call
+    // NCCL (lazy)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int nranks = 0, rank = 0;
+    cudaStream_t comm_stream = nullptr;
+    uint8_t* d_comm_buf = nullptr;
+};
+
+struct afc_merkle {
+    afc_ctx* ctx = nullptr;
+    uint64_t size = 0;
+    uint8_t* d_frontier = nullptr;   // 64 x 32
+    uint8_t* d_root = nullptr;       // 32
+    DevBuf lv[2], leaves, off;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CK(expr)                                                           \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) { set_err(ctx, _e, #expr); return AFC_ECUDA; } \
+    } while (0)
+
+void set_err(afc_ctx* ctx, cudaError_t e, const char* what) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
+}
+
+// Per-call launch log: counts launches, and when profiling is on claims a span of event pairs from the ctx pool.
+struct CallLog {
+    afc_ctx* ctx;
+    launch::LaunchLog lg;
+    int base = 0;
+    explicit CallLog(afc_ctx* c, int want = 96) : ctx(c) {
+        if (ctx->profile) {
+            base = ctx->prof_next.fetch_add(want);
+            if (base + want <= (int)ctx->prof_recs.size()) { lg.profile = true; lg.recs = ctx->prof_recs.data() + base; lg.cap = want; }
+        }
+    }
+    ~CallLog() {
+        ctx->launches += lg.n;
+        if (lg.profile && lg.used) { std::lock_guard<std::mutex> g(ctx->mu); ctx->prof_spans.emplace_back(base, lg.used); }
+    }
+    operator launch::LaunchLog*() { return &lg; }
+};
+
+struct LaneGuard {
+    afc_ctx* ctx; int idx;
+    LaneGuard(afc_ctx* c) : ctx(c), idx(-1) {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        for (;;) {
+            for (int i = 0; i < kLanes; i++) if (!ctx->lanes[i].busy) { idx = i; break; }
+            if (idx >= 0) break;
+            ctx->cv.wait(lk);
+        }
+        ctx->lanes[idx].busy = true;
+    }
+    ~LaneGuard() {
+        { std::lock_guard<std::mutex> g(ctx->mu); ctx->lanes[idx].busy = false; }
+        ctx->cv.notify_one();
+    }
+    Lane& lane() { return ctx->lanes[idx]; }
+};
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// H2D of [src, src+bytes) into dst on `st`; pageable sources go through the slot's pinned bounce buffer
+// (offset `*bounce_used` within it, advanced) so the copy is truly asynchronous.
+cudaError_t h2d(Slot& sl, void* dst, const void* src, size_t bytes, bool pinned, size_t* bounce_used) {
+    if (bytes == 0) return cudaSuccess;
+    if (pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sl.stream);
+    memcpy(sl.h_in.p + *bounce_used, src, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst, sl.h_in.p + *bounce_used, bytes, cudaMemcpyHostToDevice, sl.stream);
+    *bounce_used += (bytes + 255) & ~(size_t)255;
+    return e;
+}
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+enum Op { OP_SHA256, OP_HMAC, OP_VERIFY, OP_SIGN, OP_SIGN_EXP, OP_LEAF };
+
+struct BatchArgs {
+    Op op;
+    const uint8_t* msgs; const uint64_t* off; uint32_t n;
+    const uint8_t* a = nullptr; size_t a_item = 0;     // per-item fixed-size input (pks / seeds)
+    const uint8_t* b = nullptr; size_t b_item = 0;     // second per-item input (sigs)
+    const uint8_t* keys = nullptr; const uint32_t* koff = nullptr;   // HMAC keys
+    const uint8_t* d_expanded = nullptr; const uint32_t* key_index = nullptr;  // sign-expanded
+    uint8_t* out; size_t out_item;
+};
+
+// Generic chunked pipeline for host-buffer calls: two slots alternate so chunk c+1's H2D overlaps chunk c's kernels.
+int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
+    if (A.n == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    LaneGuard lg(ctx);
+    Lane& lane = lg.lane();
+    const bool pin_msgs = is_pinned(A.msgs), pin_off = is_pinned(A.off), pin_out = is_pinned(A.out);
+    const bool pin_a = A.a ? is_pinned(A.a) : true, pin_b = A.b ? is_pinned(A.b) : true;
+    const bool pin_keys = A.keys ? is_pinned(A.keys) : true, pin_koff = A.koff ? is_pinned(A.koff) : true;
+    const bool pin_ki = A.key_index ? is_pinned(A.key_index) : true;
+    CallLog lc(ctx, 2 * (int)(A.n / kChunkItems + 2) + 8);
+    uint32_t i0 = 0;
+    int which = 0;
+    struct Pending { uint32_t i0, cnt; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    auto drain = [&](int w) -> int {
+        if (!pend[w].active) return AFC_OK;
+        Slot& sl = lane.slot[w];
+        CK(cudaStreamSynchronize(sl.stream));
+        if (!pin_out) memcpy(A.out + (size_t)pend[w].i0 * A.out_item, sl.h_out.p, (size_t)pend[w].cnt * A.out_item);
+        pend[w].active = false;
+        return AFC_OK;
+    };
+    while (i0 < A.n) {
+        uint32_t i1 = i0;
+        uint64_t base = A.off[i0];
+        while (i1 < A.n && (i1 - i0) < kChunkItems && (A.off[i1 + 1] - base <= kChunkBytes || i1 == i0)) i1++;
+        uint32_t cnt = i1 - i0;
+        uint64_t mbytes = A.off[i1] - base;
+        Slot& sl = lane.slot[which];
+        int rc = drain(which);
+        if (rc != AFC_OK) return rc;
+        // size buffers
+        CK(sl.msgs.reserve(mbytes + 16));
+        CK(sl.off.reserve((size_t)(cnt + 1) * 8));
+        CK(sl.out.reserve((size_t)cnt * A.out_item + 16));
+        if (A.a) CK(sl.a.reserve((size_t)cnt * A.a_item + 16));
+        if (A.b) CK(sl.b.reserve((size_t)cnt * A.b_item + 16));
+        if (A.op == OP_VERIFY) CK(sl.k.reserve((size_t)cnt * 32));
+        uint32_t kbase = 0; size_t kbytes = 0;
+        if (A.op == OP_HMAC) {
+            kbase = A.koff[i0]; kbytes = A.koff[i1] - kbase;
+            CK(sl.a.reserve(kbytes + 16));
+            CK(sl.koff.reserve((size_t)(cnt + 1) * 4));
+        }
+        if (A.op == OP_SIGN_EXP && A.key_index) CK(sl.koff.reserve((size_t)cnt * 4));
+        size_t bounce = 0;
+        if (!pin_msgs) bounce += (mbytes + 255) & ~(size_t)255;
+        if (!pin_off) bounce += ((size_t)(cnt + 1) * 8 + 255) & ~(size_t)255;
+        if (A.a && !pin_a) bounce += ((size_t)cnt * A.a_item + 255) & ~(size_t)255;
+        if (A.b && !pin_b) bounce += ((size_t)cnt * A.b_item + 255) & ~(size_t)255;
+        if (A.op == OP_HMAC) { if (!pin_keys) bounce += (kbytes + 255) & ~(size_t)255; if (!pin_koff) bounce += ((size_t)(cnt + 1) * 4 + 255) & ~(size_t)255; }
+        if (A.op == OP_SIGN_EXP && A.key_index && !pin_ki) bounce += ((size_t)cnt * 4 + 255) & ~(size_t)255;
+        CK(sl.h_in.reserve(bounce + 256));
+        if (!pin_out) CK(sl.h_out.reserve((size_t)cnt * A.out_item));
+        size_t used = 0;
+        // keep the device copy of the messages congruent mod 16 with the absolute offsets so that the kernels see the
+        // same alignment whatever the chunking (d_base + off[i] == sl.msgs.p + pad + off[i] - base)
+        size_t pad = (size_t)(base & 15);
+        CK(h2d(sl, sl.msgs.p + pad, A.msgs + base, mbytes, pin_msgs, &used));
+        CK(h2d(sl, sl.off.p, A.off + i0, (size_t)(cnt + 1) * 8, pin_off, &used));
+        if (A.a) CK(h2d(sl, sl.a.p, A.a + (size_t)i0 * A.a_item, (size_t)cnt * A.a_item, pin_a, &used));
+        if (A.b) CK(h2d(sl, sl.b.p, A.b + (size_t)i0 * A.b_item, (size_t)cnt * A.b_item, pin_b, &used));
+        const uint8_t* d_base = sl.msgs.p + pad - base;     // absolute offsets stay valid
+        const uint64_t* d_off = (const uint64_t*)sl.off.p;
+        cudaError_t e = cudaSuccess;
+        switch (A.op) {
+        case OP_SHA256: e = launch::sha256_batch(d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
+        case OP_LEAF: e = launch::merkle_leaf_hashes(d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
+        case OP_HMAC: {
+            CK(h2d(sl, sl.a.p + (kbase & 3), A.keys + kbase, kbytes, pin_keys, &used));
+            CK(h2d(sl, sl.koff.p, A.koff + i0, (size_t)(cnt + 1) * 4, pin_koff, &used));
+            e = launch::hmac_sha256_batch(sl.a.p + (kbase & 3) - kbase, (const uint32_t*)sl.koff.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
+            break;
+        }
+        case OP_VERIFY:
+            e = launch::ed_verify_batch(ctx->comb, sl.a.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
+            break;
+        case OP_SIGN: e = launch::ed_sign_batch(ctx->comb, sl.a.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
+        case OP_SIGN_EXP: {
+            const uint32_t* d_ki = nullptr;
+            if (A.key_index) { CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used)); d_ki = (const uint32_t*)sl.koff.p; }
+            e = launch::ed_sign_expanded_batch(ctx->comb, A.d_expanded + (A.key_index ? 0 : (size_t)i0 * 96), d_ki, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
+            break;
+        }
+        }
+        CK(e);
+        CK(cudaMemcpyAsync(pin_out ? A.out + (size_t)i0 * A.out_item : sl.h_out.p, sl.out.p, (size_t)cnt * A.out_item,
+                           cudaMemcpyDeviceToHost, sl.stream));
+        pend[which] = {i0, cnt, true};
+        which ^= 1;
+        i0 = i1;
+    }
+    int rc = drain(0); if (rc != AFC_OK) return rc;
+    rc = drain(1); if (rc != AFC_OK) return rc;
+    return AFC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* afc_version(void) { return "afcrypto-b200 0.1.0 (sm_100a)"; }
+
+const char* afc_strerror(int rc) {
+    switch (rc) {
+    case AFC_OK: return "ok";
+    case AFC_EINVAL: return "invalid argument";
+    case AFC_ECUDA: return "CUDA failure (see afc_last_cuda_error)";
+    case AFC_ENOMEM: return "out of memory";
+    case AFC_ENCCL: return "NCCL failure or NCCL unavailable";
+    case AFC_ESTATE: return "invalid state";
+    default: return "unknown error";
+    }
+}
+
+const char* afc_last_cuda_error(afc_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+
+int afc_init(int device, afc_ctx** out) {
+    if (!out) return AFC_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return AFC_ECUDA; }
+    if (device < 0 || device >= ndev) return AFC_EINVAL;
+    afc_ctx* ctx = new (std::nothrow) afc_ctx();
+    if (!ctx) return AFC_ENOMEM;
+    ctx->device = device;
+    auto fail = [&](cudaError_t e, const char* what) { set_err(ctx, e, what); fprintf(stderr, "afc_init: %s\n", ctx->last_error.c_str()); afc_destroy(ctx); return AFC_ECUDA; };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    for (int l = 0; l < kLanes; l++)
+        for (int s = 0; s < 2; s++)
+            if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&ctx->comb, launch::ed_tables_bytes())) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
+    CallLog lc(ctx);
+    cudaStream_t s0 = ctx->lanes[0].slot[0].stream;
+    if ((e = launch::ed_build_tables(ctx->comb, s0, lc)) != cudaSuccess) return fail(e, "ed_build_tables");
+    if ((e = cudaStreamSynchronize(s0)) != cudaSuccess) return fail(e, "ed_build_tables sync");
+    *out = ctx;
+    return AFC_OK;
+}
+
+void afc_destroy(afc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    afc_comm_destroy(ctx);
+    for (int l = 0; l < kLanes; l++)
+        for (int s = 0; s < 2; s++) {
+            Slot& sl = ctx->lanes[l].slot[s];
+            if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+            sl.msgs.release(); sl.off.release(); sl.a.release(); sl.b.release(); sl.k.release(); sl.out.release(); sl.koff.release();
+            sl.h_in.release(); sl.h_out.release();
+        }
+    if (ctx->comb) cudaFree(ctx->comb);
+    for (auto& r : ctx->prof_recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+    delete ctx;
+}
+
+int afc_device_info(afc_ctx* ctx, int* sm_count, int* clock_khz, uint64_t* mem_bytes) {
+    if (!ctx) return AFC_EINVAL;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (clock_khz) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, ctx->device); *clock_khz = v; }
+    if (mem_bytes) *mem_bytes = ctx->prop.totalGlobalMem;
+    return AFC_OK;
+}
+
+uint64_t afc_launch_count(afc_ctx* ctx) { return ctx ? (uint64_t)ctx->launches.load() : 0; }
+
+void* afc_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void afc_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------- host-buffer batch calls
+int afc_sha256_batch(afc_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, uint8_t* out32) {
+    if (!ctx || !offsets || (!out32 && n) || (!msgs && n && offsets[n] != offsets[0])) return AFC_EINVAL;
+    BatchArgs A{}; A.op = OP_SHA256; A.msgs = msgs; A.off = offsets; A.n = n; A.out = out32; A.out_item = 32;
+    return run_host_batch(ctx, A);
+}
+int afc_hmac_sha256_batch(afc_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* msgs,
+                          const uint64_t* msg_off, uint32_t n, uint8_t* out32) {
+    if (!ctx || !key_off || !msg_off || (!out32 && n)) return AFC_EINVAL;
+    BatchArgs A{}; A.op = OP_HMAC; A.msgs = msgs; A.off = msg_off; A.n = n; A.keys = keys; A.koff = key_off; A.out = out32; A.out_item = 32;
+    return run_host_batch(ctx, A);
+}
+int afc_ed25519_verify_batch(afc_ctx* ctx, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs,
+                             const uint64_t* msg_off, uint32_t n, uint8_t* ok) {
+    if (!ctx || !msg_off || (n && (!pks || !sigs || !ok))) return AFC_EINVAL;
+    BatchArgs A{}; A.op = OP_VERIFY; A.msgs = msgs; A.off = msg_off; A.n = n; A.a = pks; A.a_item = 32; A.b = sigs; A.b_item = 64; A.out = ok; A.out_item = 1;
+    return run_host_batch(ctx, A);
+}
+int afc_ed25519_sign_batch(afc_ctx* ctx, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* msg_off,
+                           uint32_t n, uint8_t* sigs) {
+    if (!ctx || !msg_off || (n && (!seeds || !sigs))) return AFC_EINVAL;
+    BatchArgs A{}; A.op = OP_SIGN; A.msgs = msgs; A.off = msg_off; A.n = n; A.a = seeds; A.a_item = 32; A.out = sigs; A.out_item = 64;
+    return run_host_batch(ctx, A);
+}
+
+static int expand_common(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* out, size_t item, bool expanded) {
+    if (!ctx || (n && (!seeds || !out))) return AFC_EINVAL;
+    if (n == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    LaneGuard lg(ctx);
+    Slot& sl = lg.lane().slot[0];
+    CK(sl.a.reserve((size_t)n * 32)); CK(sl.out.reserve((size_t)n * item));
+    CK(cudaMemcpyAsync(sl.a.p, seeds, (size_t)n * 32, cudaMemcpyHostToDevice, sl.stream));
+    CallLog lc(ctx);
+    CK(launch::ed_expand_batch(ctx->comb, sl.a.p, n, expanded ? sl.out.p : nullptr, expanded ? nullptr : sl.out.p, sl.stream, lc));
+    CK(cudaMemcpyAsync(out, sl.out.p, (size_t)n * item, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    return AFC_OK;
+}
+int afc_ed25519_pubkey_batch(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* pks) { return expand_common(ctx, seeds, n, pks, 32, false); }
+int afc_ed25519_expand_batch(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* expanded96) { return expand_common(ctx, seeds, n, expanded96, 96, true); }
+
+int afc_ed25519_sign_expanded_batch(afc_ctx* ctx, const uint8_t* expanded96, const uint32_t* key_index, uint32_t n_keys,
+                                    const uint8_t* msgs, const uint64_t* msg_off, uint32_t n, uint8_t* sigs) {
+    if (!ctx || !msg_off || (n && (!expanded96 || !sigs))) return AFC_EINVAL;
+    if (!key_index && n_keys < n) return AFC_EINVAL;
+    if (key_index) for (uint32_t i = 0; i < n; i++) if (key_index[i] >= n_keys) return AFC_EINVAL;
+    if (n == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d_keys = nullptr;
+    CK(cudaMalloc(&d_keys, (size_t)n_keys * 96));
+    cudaError_t e = cudaMemcpy(d_keys, expanded96, (size_t)n_keys * 96, cudaMemcpyHostToDevice);
+    int rc = AFC_ECUDA;
+    if (e == cudaSuccess) {
+        BatchArgs A{}; A.op = OP_SIGN_EXP; A.msgs = msgs; A.off = msg_off; A.n = n; A.d_expanded = d_keys; A.key_index = key_index; A.out = sigs; A.out_item = 64;
+        rc = run_host_batch(ctx, A);
+    } else set_err(ctx, e, "cudaMemcpy(expanded keys)");
+    cudaFree(d_keys);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- device-pointer variants
+#define DEV_PROLOGUE()                                   \
+    if (!ctx) return AFC_EINVAL;                         \
+    CK(cudaSetDevice(ctx->device));                      \
+    CallLog lc(ctx);                                     \
+    cudaStream_t st = (cudaStream_t)stream;
+#define DEV_EPILOGUE() return AFC_OK;
+
+int afc_sha256_batch_dev(afc_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, uint32_t n, uint8_t* d_out32, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_out32)) return AFC_EINVAL;
+    CK(launch::sha256_batch(d_msgs, d_offsets, n, d_out32, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_hmac_sha256_batch_dev(afc_ctx* ctx, const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_msgs,
+                              const uint64_t* d_msg_off, uint32_t n, uint8_t* d_out32, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_out32)) return AFC_EINVAL;
+    CK(launch::hmac_sha256_batch(d_keys, d_key_off, d_msgs, d_msg_off, n, d_out32, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_sigs, const uint8_t* d_msgs,
+                                 const uint64_t* d_msg_off, uint32_t n, uint8_t* d_ok, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_pks) || !aligned16(d_sigs)) return AFC_EINVAL;
+    // k scratch: per-call allocation from the stream-ordered pool (freed in stream order)
+    uint32_t* d_k = nullptr;
+    if (n) CK(cudaMallocAsync((void**)&d_k, (size_t)n * 32, st));
+    cudaError_t e = launch::ed_verify_batch(ctx->comb, d_pks, d_sigs, d_msgs, d_msg_off, n, d_ok, d_k, st, lc);
+    if (n) cudaFreeAsync(d_k, st);
+    CK(e);
+    DEV_EPILOGUE();
+}
+int afc_ed25519_sign_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, const uint8_t* d_msgs, const uint64_t* d_msg_off,
+                               uint32_t n, uint8_t* d_sigs, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_seeds) || !aligned16(d_sigs)) return AFC_EINVAL;
+    CK(launch::ed_sign_batch(ctx->comb, d_seeds, d_msgs, d_msg_off, n, d_sigs, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_ed25519_pubkey_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_pks, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_seeds) || !aligned16(d_pks)) return AFC_EINVAL;
+    CK(launch::ed_expand_batch(ctx->comb, d_seeds, n, nullptr, d_pks, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_ed25519_expand_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_expanded96, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_seeds) || !aligned16(d_expanded96)) return AFC_EINVAL;
+    CK(launch::ed_expand_batch(ctx->comb, d_seeds, n, d_expanded96, nullptr, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, const uint32_t* d_key_index,
+                                        const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_expanded96) || !aligned16(d_sigs)) return AFC_EINVAL;
+    CK(launch::ed_sign_expanded_batch(ctx->comb, d_expanded96, d_key_index, d_msgs, d_msg_off, n, d_sigs, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, uint8_t* d_out32, void* stream) {
+    DEV_PROLOGUE();
+    if (!aligned16(d_out32)) return AFC_EINVAL;
+    CK(launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, d_out32, st, lc));
+    DEV_EPILOGUE();
+}
+
+// ---------------------------------------------------------------------------------- Merkle log
+int afc_merkle_new(afc_ctx* ctx, afc_merkle** out) {
+    if (!ctx || !out) return AFC_EINVAL;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    afc_merkle* m = new (std::nothrow) afc_merkle();
+    if (!m) return AFC_ENOMEM;
+    m->ctx = ctx;
+    cudaError_t e = cudaMalloc((void**)&m->d_frontier, 64 * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_root, 32);
+    if (e == cudaSuccess) e = cudaMemset(m->d_frontier, 0, 64 * 32);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_err(ctx, e, "afc_merkle_new"); afc_merkle_free(m); return AFC_ECUDA; }
+    *out = m;
+    return AFC_OK;
+}
+void afc_merkle_free(afc_merkle* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    if (m->d_frontier) cudaFree(m->d_frontier);
+    if (m->d_root) cudaFree(m->d_root);
+    m->lv[0].release(); m->lv[1].release(); m->leaves.release(); m->off.release();
+    delete m;
+}
+
+// Level schedule (host decides structure from (size, n) only; every hash runs on the device).
+// d_h: n node hashes occupying leaf positions [size, size+n).  May alias m->lv[1] but not m->lv[0].
+static int merkle_append_hashes_locked(afc_merkle* m, const uint8_t* d_h, uint32_t n, cudaStream_t st) {
+    afc_ctx* ctx = m->ctx;
+    if (n == 0) return AFC_OK;
+    if (!aligned16(d_h)) return AFC_EINVAL;
+    CallLog lc(ctx, 72);
+    uint64_t s = m->size, e = m->size + n;
+    const uint8_t* cur = d_h;
+    int h = 0, pp = 0;
+    // d_h aliasing lv[1]: first output must go to lv[0]
+    CK(m->lv[0].reserve(((size_t)n / 2 + 2) * 32));
+    while (e > s) {
+        int left = (int)(s & 1);
+        uint64_t s2 = s + left;
+        int right = (int)(e & 1);
+        uint64_t e2 = e - right;
+        uint64_t npairs = (e2 - s2) / 2;
+        DevBuf& ob = m->lv[pp];
+        CK(ob.reserve(((size_t)npairs + 2) * 32));
+        CK(launch::merkle_level(cur, ob.p, npairs, left, right, m->d_frontier, h, st, lc));
+        cur = ob.p;
+        s = s2 / 2 - left;
+        e = e2 / 2;
+        pp ^= 1;
+        h++;
+        if (h > 63) return AFC_ESTATE;
+    }
+    m->size += n;
+    return AFC_OK;
+}
+
+int afc_merkle_append_hashes_dev(afc_merkle* m, const uint8_t* d_hashes32, uint32_t n, void* stream) {
+    if (!m) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    // the level buffers are reused across calls: a caller-supplied stream must be ordered after prior work
+    return merkle_append_hashes_locked(m, d_hashes32, n, (cudaStream_t)stream);
+}
+int afc_merkle_append_dev(afc_merkle* m, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, void* stream) {
+    if (!m) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    if (n == 0) return AFC_OK;
+    CallLog lc(ctx);
+    CK(m->lv[1].reserve((size_t)n * 32));
+    CK(launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, m->lv[1].p, (cudaStream_t)stream, lc));
+    return merkle_append_hashes_locked(m, m->lv[1].p, n, (cudaStream_t)stream);
+}
+int afc_merkle_root_dev(afc_merkle* m, uint8_t* d_root32, void* stream) {
+    if (!m || !d_root32) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    CallLog lc(ctx);
+    if (!aligned16(d_root32)) return AFC_EINVAL;
+    CK(launch::merkle_root(m->d_frontier, m->size, d_root32, (cudaStream_t)stream, lc));
+    return AFC_OK;
+}
+static int merkle_root_host_locked(afc_merkle* m, uint8_t root32[32], uint64_t* tree_size) {
+    afc_ctx* ctx = m->ctx;
+    CallLog lc(ctx);
+    CK(launch::merkle_root(m->d_frontier, m->size, m->d_root, m->stream, lc));
+    if (root32) CK(cudaMemcpyAsync(root32, m->d_root, 32, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (tree_size) *tree_size = m->size;
+    return AFC_OK;
+}
+int afc_merkle_root(afc_merkle* m, uint8_t root32[32], uint64_t* tree_size) {
+    if (!m) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    return merkle_root_host_locked(m, root32, tree_size);
+}
+int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf_off, uint32_t n, uint8_t root32[32], uint64_t* tree_size) {
+    if (!m || !leaf_off) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    if (n) {
+        uint64_t base = leaf_off[0], bytes = leaf_off[n] - base;
+        if (bytes && !leaves) return AFC_EINVAL;
+        size_t pad = (size_t)(base & 15);
+        CK(m->leaves.reserve(bytes + 32)); CK(m->off.reserve((size_t)(n + 1) * 8)); CK(m->lv[1].reserve((size_t)n * 32));
+        if (bytes) CK(cudaMemcpyAsync(m->leaves.p + pad, leaves + base, bytes, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemcpyAsync(m->off.p, leaf_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, m->stream));
+        CallLog lc(ctx);
+        CK(launch::merkle_leaf_hashes(m->leaves.p + pad - base, (const uint64_t*)m->off.p, n, m->lv[1].p, m->stream, lc));
+            int rc = merkle_append_hashes_locked(m, m->lv[1].p, n, m->stream);
+        if (rc != AFC_OK) return rc;
+    }
+    return merkle_root_host_locked(m, root32, tree_size);
+}
+int afc_merkle_append_hashes(afc_merkle* m, const uint8_t* hashes32, uint32_t n, uint8_t root32[32], uint64_t* tree_size) {
+    if (!m || (n && !hashes32)) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    if (n) {
+        CK(m->lv[1].reserve((size_t)n * 32));
+        CK(cudaMemcpyAsync(m->lv[1].p, hashes32, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+        int rc = merkle_append_hashes_locked(m, m->lv[1].p, n, m->stream);
+        if (rc != AFC_OK) return rc;
+    }
+    return merkle_root_host_locked(m, root32, tree_size);
+}
+int afc_merkle_save(afc_merkle* m, uint8_t* state) {
+    if (!m || !state) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamSynchronize(m->stream));
+    memcpy(state, &m->size, 8);
+    CK(cudaMemcpy(state + 8, m->d_frontier, 64 * 32, cudaMemcpyDeviceToHost));
+    for (int h = 0; h < 64; h++) if (!((m->size >> h) & 1)) memset(state + 8 + 32 * h, 0, 32);
+    return AFC_OK;
+}
+int afc_merkle_load(afc_merkle* m, const uint8_t* state) {
+    if (!m || !state) return AFC_EINVAL;
+    afc_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamSynchronize(m->stream));
+    memcpy(&m->size, state, 8);
+    CK(cudaMemcpy(m->d_frontier, state + 8, 64 * 32, cudaMemcpyHostToDevice));
+    return AFC_OK;
+}
+
+// ---------------------------------------------------------------------------------- NCCL (dlopen, optional)
+namespace {
+struct nccl_id_t { char internal[128]; };
+typedef int (*fn_get_uid)(nccl_id_t*);
+typedef int (*fn_init_rank)(void**, int, nccl_id_t, int);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+void* nccl_open() {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // reuse the copy torch already loaded, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return h;
+}
+}  // namespace
+
+int afc_comm_unique_id(uint8_t id128[128]) {
+    void* h = nccl_open();
+    if (!h) return AFC_ENCCL;
+    fn_get_uid f = (fn_get_uid)dlsym(h, "ncclGetUniqueId");
+    if (!f) return AFC_ENCCL;
+    nccl_id_t id;
+    if (f(&id) != 0) return AFC_ENCCL;
+    memcpy(id128, id.internal, 128);
+    return AFC_OK;
+}
+int afc_comm_init(afc_ctx* ctx, int nranks, int rank, const uint8_t id128[128]) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return AFC_EINVAL;
+    if (ctx->nccl_comm) return AFC_ESTATE;
+    CK(cudaSetDevice(ctx->device));
+    ctx->nccl_lib = nccl_open();
+    if (!ctx->nccl_lib) return AFC_ENCCL;
+    fn_init_rank f = (fn_init_rank)dlsym(ctx->nccl_lib, "ncclCommInitRank");
+    if (!f) return AFC_ENCCL;
+    nccl_id_t id; memcpy(id.internal, id128, 128);
+    if (f(&ctx->nccl_comm, nranks, id, rank) != 0) { ctx->nccl_comm = nullptr; return AFC_ENCCL; }
+    ctx->nranks = nranks; ctx->rank = rank;
+    CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void**)&ctx->d_comm_buf, (size_t)(nranks + 1) * 32));
+    return AFC_OK;
+}
+int afc_comm_allgather_roots(afc_ctx* ctx, const uint8_t local_root32[32], uint8_t* all_roots) {
+    if (!ctx || !local_root32 || !all_roots) return AFC_EINVAL;
+    if (!ctx->nccl_comm) return AFC_ESTATE;
+    CK(cudaSetDevice(ctx->device));
+    fn_allgather f = (fn_allgather)dlsym(ctx->nccl_lib, "ncclAllGather");
+    if (!f) return AFC_ENCCL;
+    uint8_t* send = ctx->d_comm_buf + (size_t)ctx->nranks * 32;
+    CK(cudaMemcpyAsync(send, local_root32, 32, cudaMemcpyHostToDevice, ctx->comm_stream));
+    if (f(send, ctx->d_comm_buf, 32, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->comm_stream) != 0) return AFC_ENCCL;
+    CK(cudaMemcpyAsync(all_roots, ctx->d_comm_buf, (size_t)ctx->nranks * 32, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    CK(cudaStreamSynchronize(ctx->comm_stream));
+    return AFC_OK;
+}
+int afc_comm_destroy(afc_ctx* ctx) {
+    if (!ctx) return AFC_EINVAL;
+    if (ctx->nccl_comm) {
+        fn_destroy f = (fn_destroy)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+        if (f) f(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
+    if (ctx->d_comm_buf) { cudaFree(ctx->d_comm_buf); ctx->d_comm_buf = nullptr; }
+    return AFC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------- per-kernel event profiling
+int afc_profile_begin(afc_ctx* ctx, int max_launches) {
+    if (!ctx || max_launches <= 0) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->profile) return AFC_ESTATE;
+    size_t old = ctx->prof_recs.size();
+    if ((size_t)max_launches > old) {
+        ctx->prof_recs.resize(max_launches);
+        for (size_t i = old; i < ctx->prof_recs.size(); i++) {
+            ctx->prof_recs[i].name = nullptr;
+            if (cudaEventCreate(&ctx->prof_recs[i].e0) != cudaSuccess || cudaEventCreate(&ctx->prof_recs[i].e1) != cudaSuccess) return AFC_ECUDA;
+        }
+    }
+    ctx->prof_next = 0;
+    ctx->prof_spans.clear();
+    ctx->profile = true;
+    return AFC_OK;
+}
+int afc_profile_end(afc_ctx* ctx, afc_profile_entry* out, int cap) {
+    if (!ctx || (cap > 0 && !out)) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->profile) return AFC_ESTATE;
+    ctx->profile = false;
+    int n_out = 0;
+    for (auto& sp : ctx->prof_spans) {
+        for (int i = 0; i < sp.second; i++) {
+            launch::LaunchRec& r = ctx->prof_recs[sp.first + i];
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+            int k = 0;
+            for (; k < n_out; k++) if (strncmp(out[k].name, r.name, sizeof(out[k].name) - 1) == 0) break;
+            if (k == n_out) {
+                if (n_out >= cap) continue;
+                memset(&out[k], 0, sizeof(out[k]));
+                strncpy(out[k].name, r.name, sizeof(out[k].name) - 1);
+                out[k].min_ms = ms; out[k].max_ms = ms;
+                n_out++;
+            }
+            out[k].count++;
+            out[k].total_ms += ms;
+            if (ms < out[k].min_ms) out[k].min_ms = ms;
+            if (ms > out[k].max_ms) out[k].max_ms = ms;
+        }
+    }
+    ctx->prof_spans.clear();
+    return n_out;
+}
+
+// ---------------------------------------------------------------------------------- diagnostics
+int afc_selftest(afc_ctx* ctx, uint32_t iters) {
+    if (!ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    CK(cudaMalloc((void**)&d, 4));
+    CK(cudaMemset(d, 0, 4));
+    CallLog lc(ctx);
+    cudaError_t e = launch::ed_selftest(iters, d, 0, lc);
+    uint32_t bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, d, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    return (int)bad;
+}
+int afc_microbench(afc_ctx* ctx, int which, uint32_t iters, double* ops_per_s, double* ms_out) {
+    if (!ctx || !ops_per_s) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    CK(cudaMalloc((void**)&d, 4));
+    const uint32_t threads = 128;
+    const uint32_t blocks = (uint32_t)ctx->prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CallLog lc(ctx);
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 2 && e == cudaSuccess; rep++) {      // first pass warms up
+        cudaEventRecord(e0, 0);
+        if (which == 3 || which == 4) e = launch::microbench_hash(which, iters, blocks, threads, d, 0, lc);
+        else e = launch::microbench_fe(which, iters, blocks, threads, d, 0, lc);
+        cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    }
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    CK(e);
+    double per_thread = (which == 3 || which == 4) ? 1.0 : 2.0;   // fe probes do two ops per iteration
+    *ops_per_s = (double)blocks * threads * iters * per_thread / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return AFC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// Ed25519 kernels for sm_100a: batched verify (the headline metric), sign, key expansion.
+//
+// Reference call sites replaced (relative to /root/reference/control-plane):
+//   ed25519.Verify            internal/services/vc_service.go:504,1624; internal/cli/vc_verification_enhanced.go:453
+//   ed25519.Sign              internal/services/vc_service.go:463,715
+//   ed25519.NewKeyFromSeed    internal/services/vc_service.go:460,712; internal/services/did_service.go:523
+//
+// Verify is two kernels so that each gets its own register/occupancy point:
+//   k_ed_hram    k_i = SHA-512(R_i || A_i || M_i) mod L            (streams the message; 64-bit ALU work)
+//   k_ed_verify  R'_i = [S_i]B + [k_i](-A_i); ok_i = enc(R'_i) == R_i  (pure 32-bit IMAD/IADD3 work,
+//                ~2.9k field multiplications per credential — >99% of the time)
+// One credential per thread; fixed 4-bit windows keep all 32 lanes on one instruction stream.
+#include "afc_launch.h"
+#include "afc_ge.cuh"
+
+namespace afc {
+
+static constexpr int ED_THREADS = 128;
+
+__device__ __forceinline__ void load_words8(uint32_t* w, const uint8_t* p) {
+    const uint4* q = (const uint4*)p;
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void store_words8(uint8_t* p, const uint32_t* w) {
+    uint4* q = (uint4*)p;
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+__global__ void k_ed_build_tables(ge_precomp* comb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64) ge_build_comb_row(comb + 8 * i, i);
+}
+
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
+          const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pk[8], sig[16], k[8];
+    load_words8(pk, pks + 32ull * i);
+    load_words8(sig, sigs + 64ull * i);          // only R is hashed
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    ed25519_hram(k, pk, sig, msgs + o0, o1 - o0);
+    store_words8((uint8_t*)(k_out + 8ull * i), k);
+}
+
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs,
+            const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
+    __shared__ ge_precomp sB[8];                 // (j+1)B, j = 0..7: 768 bytes
+    {
+        const uint32_t* src = (const uint32_t*)comb;
+        uint32_t* dst = (uint32_t*)sB;
+        for (int t = threadIdx.x; t < (int)(sizeof(sB) / 4); t += blockDim.x) dst[t] = src[t];
+    }
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pk[8], sig[16], k[8];
+    load_words8(pk, pks + 32ull * i);
+    load_words8(sig, sigs + 64ull * i);
+    load_words8(sig + 8, sigs + 64ull * i + 32);
+    load_words8(k, (const uint8_t*)(ks + 8ull * i));
+    ok[i] = (uint8_t)ed25519_verify_core(pk, sig, k, sB);
+}
+
+// mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, int mode,
+          const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n, uint8_t* __restrict__ sigs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8], prefix[8], pk[8], sig[16];
+    if (mode == 0) {
+        uint32_t seed[8];
+        load_words8(seed, keys + 32ull * i);
+        ed25519_expand(s, prefix, pk, seed, comb);
+    } else {
+        const uint8_t* e = keys + 96ull * (key_index ? key_index[i] : i);
+        load_words8(s, e); load_words8(prefix, e + 32); load_words8(pk, e + 64);
+    }
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    ed25519_sign_expanded(sig, s, prefix, pk, msgs + o0, o1 - o0, comb);
+    store_words8(sigs + 64ull * i, sig);
+    store_words8(sigs + 64ull * i + 32, sig + 8);
+}
+
+// seeds -> expanded96 (s || prefix || pk) and/or pks (32 B each)
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_expand(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ seeds, uint32_t n, uint8_t* __restrict__ expanded96,
+            uint8_t* __restrict__ pks) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t seed[8], s[8], prefix[8], pk[8];
+    load_words8(seed, seeds + 32ull * i);
+    ed25519_expand(s, prefix, pk, seed, comb);
+    if (expanded96) {
+        uint8_t* e = expanded96 + 96ull * i;
+        store_words8(e, s); store_words8(e + 32, prefix); store_words8(e + 64, pk);
+    }
+    if (pks) store_words8(pks + 32ull * i, pk);
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t xorshift(uint32_t& x) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; }
+
+// PTX field arithmetic vs the portable versions, on random and boundary operands
+__global__ void k_ed_selftest(uint32_t iters, uint32_t* mismatch) {
+    uint32_t rs = 0x9E3779B9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
+    uint32_t bad = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        fe a, b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a.v[i] = xorshift(rs); b.v[i] = xorshift(rs); }
+        uint32_t sel = xorshift(rs);
+        if ((sel & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) a.v[i] = 0xffffffffu;
+        }
+        if ((sel & 0xf0) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu;
+        }
+        if ((sel & 0xf00) == 0) { fe_0(a); a.v[0] = sel >> 26; }
+        if ((sel & 0xf000) == 0) {
+#pragma unroll
+            for (int i = 1; i < 8; i++) b.v[i] = 0xffffffffu;
+            b.v[0] = 0xffffffffu - (sel >> 26);
+        }
+        fe r1, r2;
+        uint32_t w1[8], w2[8];
+        fe_mul(r1, a, b); fe_mul_c(r2, a, b); fe_towords(w1, r1); fe_towords(w2, r2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) bad |= w1[i] ^ w2[i];
+        fe_sq(r1, a); fe_mul_c(r2, a, a); fe_towords(w1, r1); fe_towords(w2, r2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) bad |= w1[i] ^ w2[i];
+        fe_add(r1, a, b); fe_add_c(r2, a, b);
+#pragma unroll
+        for (int i = 0; i < 8; i++) bad |= r1.v[i] ^ r2.v[i];
+        fe_sub(r1, a, b); fe_sub_c(r2, a, b);
+#pragma unroll
+        for (int i = 0; i < 8; i++) bad |= r1.v[i] ^ r2.v[i];
+    }
+    if (bad) atomicAdd(mismatch, 1u);
+}
+
+// register-only throughput probes: which = 0 fe_mul, 1 fe_sq, 2 fe_add+fe_sub, 5 fe_mul_c, 6 fe_sq via mul
+__global__ void k_microbench_fe(int which, uint32_t iters, uint32_t* sink) {
+    uint32_t rs = 0x9E3779B9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
+    fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = xorshift(rs); b.v[i] = xorshift(rs); }
+    if (which == 0) {
+        for (uint32_t it = 0; it < iters; it++) { fe_mul(a, a, b); fe_mul(b, b, a); }
+    } else if (which == 1) {
+        for (uint32_t it = 0; it < iters; it++) { fe_sq(a, a); fe_sq(b, b); }
+    } else if (which == 2) {
+        for (uint32_t it = 0; it < iters; it++) { fe_add(a, a, b); fe_sub(b, b, a); }
+    } else if (which == 5) {
+        for (uint32_t it = 0; it < iters; it++) { fe_mul_c(a, a, b); fe_mul_c(b, b, a); }
+    } else {
+        for (uint32_t it = 0; it < iters; it++) { fe_mul(a, a, a); fe_mul(b, b, b); }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a.v[i] ^ b.v[i];
+    if (x == 0x12345678u) sink[0] = x;
+}
+
+namespace launch {
+
+static inline uint32_t blocks_for(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
+
+size_t ed_tables_bytes() { return sizeof(ge_precomp) * 64 * 8; }
+
+cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<2, 32, 0, s>>>((ge_precomp*)comb));
+    return cudaGetLastError();
+}
+cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
+                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+    AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, pks, sigs, scratch_k, n, ok));
+    return cudaGetLastError();
+}
+cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                          uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, nullptr, 0, msgs, off, n, sigs));
+    return cudaGetLastError();
+}
+cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, const uint32_t* key_index, const uint8_t* msgs,
+                                   const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, expanded96, key_index, 1, msgs, off, n, sigs));
+    return cudaGetLastError();
+}
+cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
+                            cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_expand", s, k_ed_expand<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, n, expanded96, pks_only));
+    return cudaGetLastError();
+}
+cudaError_t ed_selftest(uint32_t iters, uint32_t* d_mismatch, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_ed_selftest", s, k_ed_selftest<<<64, 128, 0, s>>>(iters, d_mismatch));
+    return cudaGetLastError();
+}
+cudaError_t microbench_fe(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_microbench_fe", s, k_microbench_fe<<<blocks, threads, 0, s>>>(which, iters, sink));
+    return cudaGetLastError();
+}
+
+}  // namespace launch
+}  // namespace afc

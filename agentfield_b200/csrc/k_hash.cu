@@ -1,0 +1,172 @@
+// SHA-256 / HMAC-SHA256 / RFC 6962 Merkle kernels for sm_100a.
+//
+// Reference call sites replaced (relative to /root/reference/control-plane):
+//   k_sha256_batch       sha256.Sum256 in VCService.hashData        internal/services/vc_service.go:508-515
+//                        payload digest                              internal/services/payload_store.go:69-94
+//                        seed derivation hash                        internal/services/did_service.go:515-521
+//   k_hmac_sha256_batch  generateWebhookSignature                    internal/services/webhook_dispatcher.go:470-474
+//   k_merkle_*           NEW (RFC 6962 §2.1); reference stub         internal/cli/vc_verification_enhanced.go:531-534
+//
+// Shape: one message per thread; every lane runs the identical fully-unrolled compression (SHF funnel
+// rotates, LOP3 Ch/Maj, round constants as constant-bank immediates).  These kernels are integer-ALU
+// bound (~1.5k ALU ops per 64-byte block => ~20 ops/byte), an order of magnitude above the HBM
+// roofline's ops/byte; see DESIGN.md §kernels.
+#include "afc_launch.h"
+#include "afc_sha.cuh"
+
+namespace afc {
+
+static constexpr int HASH_THREADS = 128;
+
+__global__ void __launch_bounds__(HASH_THREADS)
+k_sha256_batch(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    uint32_t st[8];
+    sha256_msg(st, msgs + o0, o1 - o0);
+    store_digest256(out + 32ull * i, st);
+}
+
+__global__ void __launch_bounds__(HASH_THREADS)
+k_hmac_sha256_batch(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ koff, const uint8_t* __restrict__ msgs,
+                    const uint64_t* __restrict__ off, uint32_t n, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k0 = koff[i], k1 = koff[i + 1];
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    uint32_t st[8];
+    hmac_sha256_msg(st, keys + k0, k1 - k0, msgs + o0, o1 - o0);
+    store_digest256(out + 32ull * i, st);
+}
+
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_leaf(const uint8_t* __restrict__ leaves, const uint64_t* __restrict__ off, uint32_t n, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    uint32_t st[8];
+    sha256_merkle_leaf(st, leaves + o0, o1 - o0);
+    store_digest256(out + 32ull * i, st);
+}
+
+__device__ __forceinline__ void load_node(uint32_t w[8], const uint8_t* p) {
+    const uint4* q = (const uint4*)p;       // node arrays are 32-byte records in 16B-aligned buffers
+    uint4 a = q[0], b = q[1];
+    w[0] = bswap32(a.x); w[1] = bswap32(a.y); w[2] = bswap32(a.z); w[3] = bswap32(a.w);
+    w[4] = bswap32(b.x); w[5] = bswap32(b.y); w[6] = bswap32(b.z); w[7] = bswap32(b.w);
+}
+
+// One level of the RFC 6962 tree over an index range (see afc_launch.h for the meaning of the flags).
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_level(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t npairs, int left_merge, int right_orphan,
+               uint8_t* frontier, int h) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t first = left_merge ? 1 : 0;
+    if (p < npairs) {
+        uint32_t l[8], r[8], o[8];
+        load_node(l, in + 32 * (first + 2 * p));
+        load_node(r, in + 32 * (first + 2 * p + 1));
+        sha256_merkle_node(o, l, r);
+        store_digest256(out + 32 * (first + p), o);
+    } else if (p == npairs) {
+        if (left_merge) {
+            uint32_t l[8], r[8], o[8];
+            load_node(l, frontier + 32 * h);
+            load_node(r, in);
+            sha256_merkle_node(o, l, r);
+            store_digest256(out, o);
+        }
+        if (right_orphan) {
+            const uint4* src = (const uint4*)(in + 32 * (first + 2 * npairs));
+            uint4 a = src[0], b = src[1];
+            uint4* dst = (uint4*)(frontier + 32 * h);
+            dst[0] = a; dst[1] = b;
+        }
+    }
+}
+
+__global__ void k_merkle_root(const uint8_t* __restrict__ frontier, uint64_t size, uint8_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t acc[8];
+    if (size == 0) {
+        sha256_msg(acc, (const uint8_t*)0, 0);
+    } else {
+        int h = 0;
+        while (!((size >> h) & 1)) h++;
+        load_node(acc, frontier + 32 * h);
+        for (h = h + 1; h < 64; h++) {
+            if ((size >> h) & 1) {
+                uint32_t l[8], o[8];
+                load_node(l, frontier + 32 * h);
+                sha256_merkle_node(o, l, acc);
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = o[i];
+            }
+        }
+    }
+    store_digest256(out, acc);
+}
+
+// register-only throughput probes: which = 3 SHA-256 compress, 4 SHA-512 compress
+__global__ void k_microbench_hash(int which, uint32_t iters, uint32_t* sink) {
+    uint32_t seed = blockIdx.x * blockDim.x + threadIdx.x;
+    if (which == 3) {
+        uint32_t st[8], w[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = seed + i;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = st[i & 7] ^ (it + i);
+            sha256_compress(st, w);
+        }
+        if (st[0] == 0x12345678u) sink[0] = st[1];
+    } else {
+        uint64_t st[8], w[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = seed + i;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = st[i & 7] ^ (it + i);
+            sha512_compress(st, w);
+        }
+        if (st[0] == 0x12345678u) sink[0] = (uint32_t)st[1];
+    }
+}
+
+namespace launch {
+
+static inline uint32_t blocks_for(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
+
+cudaError_t sha256_batch(const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_sha256_batch", s, k_sha256_batch<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(msgs, off, n, out32));
+    return cudaGetLastError();
+}
+cudaError_t hmac_sha256_batch(const uint8_t* keys, const uint32_t* koff, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                              uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_hmac_sha256_batch", s, k_hmac_sha256_batch<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(keys, koff, msgs, off, n, out32));
+    return cudaGetLastError();
+}
+cudaError_t merkle_leaf_hashes(const uint8_t* leaves, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_merkle_leaf", s, k_merkle_leaf<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(leaves, off, n, out32));
+    return cudaGetLastError();
+}
+cudaError_t merkle_level(const uint8_t* in, uint8_t* out, uint64_t npairs, int left_merge, int right_orphan,
+                         uint8_t* frontier, int h, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_merkle_level", s, k_merkle_level<<<blocks_for(npairs + 1, HASH_THREADS), HASH_THREADS, 0, s>>>(in, out, npairs, left_merge, right_orphan, frontier, h));
+    return cudaGetLastError();
+}
+cudaError_t merkle_root(const uint8_t* frontier, uint64_t size, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_merkle_root", s, k_merkle_root<<<1, 32, 0, s>>>(frontier, size, out32));
+    return cudaGetLastError();
+}
+cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_microbench_hash", s, k_microbench_hash<<<blocks, threads, 0, s>>>(which, iters, sink));
+    return cudaGetLastError();
+}
+
+}  // namespace launch
+}  // namespace afc

@@ -23,6 +23,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 #define AFC_OK 0
 #define AFC_EINVAL (-1) /* bad argument / bad length (e.g. Go would panic on len(pk) != 32) */
@@ -144,8 +147,21 @@ int afc_comm_destroy(afc_ctx* ctx);
  * afc_microbench: register-only throughput of a primitive; which = 0 fe_mul, 1 fe_sq, 2 fe_add,
  * 3 sha256 compress, 4 sha512 compress; returns primitive-ops per second (whole GPU) in *ops_per_s. */
 int afc_selftest(afc_ctx* ctx, uint32_t iters);
+/* Per-kernel CUDA-event timing (tracing hook): between begin and end every kernel this ctx launches is
+ * bracketed by two events on its own stream; afc_profile_end synchronises the device and returns one aggregated entry
+ * per kernel name (returns the number of entries, or a negative error). */
+typedef struct afc_profile_entry {
+    char name[48];
+    uint32_t count;
+    double total_ms, min_ms, max_ms;
+} afc_profile_entry;
+int afc_profile_begin(afc_ctx* ctx, int max_launches);
+int afc_profile_end(afc_ctx* ctx, afc_profile_entry* out, int cap);
 int afc_microbench(afc_ctx* ctx, int which, uint32_t iters, double* ops_per_s, double* ms);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

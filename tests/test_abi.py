@@ -1,0 +1,65 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/afcrypto.h
+declares, refuses to run without a device (no CPU fallback), and the product never touches oracle/."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "afcrypto.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(afc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from agentfield_b200 import _abi
+    lib = _abi.load()
+    names = _declared()
+    assert len(names) >= 38
+    for n in names:
+        assert hasattr(lib, n), "libafcrypto.so does not export %s" % n
+    assert set(names) == set(_abi.SYMBOLS), "ctypes table and header disagree: %s" % (set(names) ^ set(_abi.SYMBOLS))
+    assert b"sm_100a" in lib.afc_version()
+    assert lib.afc_strerror(-2).startswith(b"CUDA")
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path needs a CPU-only box")
+    import agentfield_b200 as afb
+    with pytest.raises(afb.AfcError) as ei:
+        afb.Context(0)
+    assert ei.value.rc == afb._abi.AFC_ECUDA
+    lib = afb._abi.load()
+    out = (C.c_uint8 * 32)()
+    off = (C.c_uint64 * 2)(0, 0)
+    assert lib.afc_sha256_batch(None, None, off, 1, out) == afb._abi.AFC_EINVAL     # NULL ctx: nothing computes
+
+
+def test_product_never_imports_or_links_the_oracle():
+    pkg = os.path.join(ROOT, "agentfield_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", "Makefile")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("oracle/", "ORACLE_DIR_MENTION") or f in ("__init__.py",) or \
+                    all("import" not in ln and "#include" not in ln for ln in txt.splitlines() if "oracle" in ln), (d, f)
+                assert "hostsim" not in txt or f.endswith((".cuh", ".cu")), (d, f)
+    # and the shared object carries no oracle / OpenSSL symbols
+    import subprocess
+    syms = subprocess.check_output(["nm", "-D", os.path.join(pkg, "libafcrypto.so")]).decode()
+    assert "afo_" not in syms and "afx_" not in syms and "EVP_" not in syms and "hs_verify" not in syms
+    ldd = subprocess.check_output(["ldd", os.path.join(pkg, "libafcrypto.so")]).decode()
+    assert "libcrypto" not in ldd and "libafc_oracle" not in ldd
+
+
+def test_kernels_are_sm100a_sass():
+    import subprocess
+    so = os.path.join(ROOT, "agentfield_b200", "libafcrypto.so")
+    out = subprocess.check_output(["cuobjdump", "-lelf", so]).decode()
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out

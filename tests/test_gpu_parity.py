@@ -1,0 +1,350 @@
+"""GPU parity tests — the CUDA path, through the C ABI (libafcrypto.so), against the oracle and the golden fixtures.
+Bit-exact bar: every byte / index must match (integer work; no tolerance).  Nothing here reads /root/reference."""
+import hashlib
+import hmac
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import c_oracle as CO, go_ed25519 as G, merkle as OM
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(msgs):
+    from agentfield_b200 import pack
+    return pack(msgs)
+
+
+def test_native_library_is_what_runs(ctx):
+    import agentfield_b200 as afb
+    assert afb.LIB_PATH.endswith("libafcrypto.so")
+    info = ctx.device_info()
+    assert info["sm_count"] >= 100
+    before = ctx.launch_count()
+    buf, off = _pack([b"abc"])
+    assert ctx.sha256_packed(buf, off)[0].tobytes() == hashlib.sha256(b"abc").digest()
+    assert ctx.launch_count() > before                      # a kernel really launched
+
+
+def test_ptx_field_arithmetic_selftest(ctx):
+    """Inline-PTX carry-chain field arithmetic vs the portable versions, on the device (random + boundary operands)."""
+    assert ctx.selftest(3000) == 0
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def test_golden_fips180_sha256(ctx):
+    es = [e for e in golden("fips180.json") if e["alg"] == "sha256"]
+    msgs = [bytes.fromhex(e["repeat"]) * e["count"] if "repeat" in e else bytes.fromhex(e["msg"]) for e in es]
+    buf, off = _pack(msgs)
+    out = ctx.sha256_packed(buf, off)
+    for e, o in zip(es, out):
+        assert o.tobytes().hex() == e["digest"], e["source"]
+
+
+def test_golden_rfc4231_hmac(ctx):
+    from agentfield_b200 import MAC
+    es = golden("rfc4231.json")
+    tags = MAC(ctx).hmac_sha256_batch([bytes.fromhex(e["key"]) for e in es], [bytes.fromhex(e["msg"]) for e in es])
+    for e, t in zip(es, tags):
+        assert t.hex() == e["tag"], e["name"]
+
+
+def test_golden_rfc8032_sign_verify_pubkey(ctx):
+    from agentfield_b200 import Signer, Verifier
+    es = golden("rfc8032.json")
+    seeds = [bytes.fromhex(e["seed"]) for e in es]
+    msgs = [bytes.fromhex(e["msg"]) for e in es]
+    assert [s.hex() for s in Signer(ctx).sign_batch(seeds, msgs)] == [e["sig"] for e in es]
+    assert [p.hex() for p in Signer(ctx).public_keys(seeds)] == [e["pk"] for e in es]
+    ok = Verifier(ctx).verify_batch([bytes.fromhex(e["pk"]) for e in es], msgs, [bytes.fromhex(e["sig"]) for e in es])
+    assert all(ok)
+
+
+def test_golden_ed25519_edge_set_go_rules(ctx):
+    """S = L, S + L, sig[63] high bits, non-canonical R / A, small-order A, A off-curve, x = 0 with sign bit, bit flips:
+    the GPU must accept/reject exactly as Go does."""
+    from agentfield_b200 import Verifier
+    es = golden("ed25519_edge.json")
+    ok = Verifier(ctx).verify_batch([bytes.fromhex(e["pk"]) for e in es], [bytes.fromhex(e["msg"]) for e in es],
+                                    [bytes.fromhex(e["sig"]) for e in es])
+    for e, o in zip(es, ok):
+        assert o == e["valid"], e["name"]
+    assert sum(ok) >= 10
+
+
+def test_golden_rfc6962_roots(ctx):
+    from agentfield_b200 import Auditor
+    g = golden("rfc6962.json")
+    leaves = [bytes.fromhex(x) for x in g["leaves"]]
+    a = Auditor(ctx)
+    assert a.root() == (bytes.fromhex(g["empty_root"]), 0)
+    for n in range(1, 9):                                   # one leaf at a time: exercises every frontier merge
+        root, size = a.append([leaves[n - 1]])
+        assert size == n and root.hex() == g["roots"][n - 1]
+    for s in g["synthetic"]:
+        if s["leaves"] is not None:
+            b = Auditor(ctx)
+            root, size = b.append([bytes.fromhex(x) for x in s["leaves"]])
+            assert size == s["n"] and root.hex() == s["root"]
+            b.close()
+    a.close()
+
+
+def test_golden_reference_flow(ctx):
+    """derivePrivateKey -> did:key, hashData, and a VC-shaped canonical message (reference_flow.json)."""
+    from agentfield_b200 import Hasher, Signer, Verifier
+    g = golden("reference_flow.json")
+    master = bytes.fromhex(g["master_seed"])
+    seeds = Hasher(ctx).sha256_batch([master + d["path"].encode() for d in g["derivations"]])
+    assert [s.hex() for s in seeds] == [d["seed"] for d in g["derivations"]]
+    assert [p.hex() for p in Signer(ctx).public_keys(seeds)] == [d["pk"] for d in g["derivations"]]
+    digs = Hasher(ctx).sha256_batch([bytes.fromhex(h["marshalled"]) for h in g["hash_data"]])
+    import base64
+    assert [base64.urlsafe_b64encode(d).rstrip(b"=").decode() for d in digs] == [h["hash"] for h in g["hash_data"]]
+    vc = g["vc"]
+    msg = vc["canonical"].encode()
+    assert Signer(ctx).sign_batch([bytes.fromhex(vc["seed"])], [msg])[0].hex() == vc["sig"]
+    assert Verifier(ctx).verify_batch([bytes.fromhex(vc["pk"])], [msg], [bytes.fromhex(vc["sig"])]) == [True]
+
+
+# ----------------------------------------------------------------------------- randomised parity vs the oracle
+def test_sha256_hmac_ragged_lengths_and_alignments(ctx):
+    rng = np.random.default_rng(0xAF03)
+    lens = list(range(0, 200)) + [255, 256, 257, 511, 512, 513, 1000, 1300, 4096, 70000] + [int(x) for x in rng.integers(0, 3000, 300)]
+    msgs = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]        # packed back to back => every alignment
+    buf, off = _pack(msgs)
+    out = ctx.sha256_packed(buf, off)
+    assert (out == CO.sha256_batch(buf, off, 4)).all()
+    assert out[3].tobytes() == hashlib.sha256(msgs[3]).digest()
+    klens = [int(x) for x in rng.integers(0, 200, len(msgs))]
+    klens[:8] = [0, 1, 63, 64, 65, 131, 4096, 32]
+    keys = [rng.integers(0, 256, k, dtype=np.uint8).tobytes() for k in klens]
+    from agentfield_b200 import pack32
+    kb, ko = pack32(keys)
+    tags = ctx.hmac_sha256_packed(kb, ko, buf, off)
+    assert (tags == CO.hmac_sha256_batch(kb, ko, buf, off, 4)).all()
+    assert tags[6].tobytes() == hmac.new(keys[6], msgs[6], hashlib.sha256).digest()
+
+
+def test_empty_batches(ctx):
+    from agentfield_b200 import Auditor
+    z8, off0 = np.zeros(1, np.uint8), np.zeros(1, np.uint64)
+    assert ctx.sha256_packed(z8, off0).shape == (0, 32)
+    assert ctx.verify_packed(np.zeros((0, 32), np.uint8), np.zeros((0, 64), np.uint8), z8, off0).shape == (0,)
+    assert ctx.sign_packed(np.zeros((0, 32), np.uint8), z8, off0).shape == (0, 64)
+    a = Auditor(ctx)
+    assert a.append([]) == (hashlib.sha256(b"").digest(), 0)
+    a.close()
+
+
+def test_ed25519_random_parity_ragged(ctx):
+    rng = np.random.default_rng(0xAF02)
+    n = 3000
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    lens = rng.integers(0, 1400, n)
+    lens[:6] = [0, 1, 63, 64, 65, 1300]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    buf = rng.integers(0, 256, int(off[-1]) + 1, dtype=np.uint8)
+    sigs = ctx.sign_packed(seeds, buf, off)
+    assert (sigs == CO.ed25519_sign_batch(seeds, buf, off, 8)).all()
+    pks = ctx.pubkeys(seeds)
+    assert (pks == CO.ed25519_pubkey_batch(seeds, 8)).all()
+    # corrupt a third of the items in different places (sig R, sig S, pk, message)
+    s2, p2, b2 = sigs.copy(), pks.copy(), buf.copy()
+    idx = np.arange(n)
+    s2[idx % 9 == 0, 5] ^= 0x01
+    s2[idx % 9 == 3, 40] ^= 0x80
+    p2[idx % 9 == 6, 1] ^= 0x04
+    for i in idx[(idx % 9 == 7) & (lens > 0)]:
+        b2[int(off[i])] ^= 0x40
+    ok = ctx.verify_packed(p2, s2, b2, off)
+    exp = CO.ed25519_verify_batch(p2, s2, b2, off, 8)
+    assert (ok == exp).all()
+    assert 0.55 * n < ok.sum() < 0.7 * n
+
+
+def test_expanded_key_cache_sign(ctx):
+    rng = np.random.default_rng(0xAF11)
+    nk, n = 16, 500
+    seeds = rng.integers(0, 256, (nk, 32), dtype=np.uint8)
+    exp96 = ctx.expand(seeds)
+    assert (exp96[:, 64:] == CO.ed25519_pubkey_batch(seeds)).all()
+    ki = (np.arange(n) % nk).astype(np.uint32)
+    msgs = rng.integers(0, 256, (n, 512), dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * 512
+    sigs = ctx.sign_expanded_packed(exp96, ki, msgs.reshape(-1), off)
+    assert (sigs == CO.ed25519_sign_batch(seeds[ki], msgs.reshape(-1), off, 8)).all()
+
+
+def test_merkle_incremental_appends_match_oracle(ctx):
+    """Random (size, n) appends: every frontier merge / orphan case of the level schedule."""
+    from agentfield_b200 import Auditor
+    rng = np.random.default_rng(0xAF04)
+    for trial in range(6):
+        a = Auditor(ctx)
+        leaves = []
+        for step in range(10):
+            k = int(rng.integers(1, 70)) if trial < 4 else int(rng.integers(1, 3000))
+            new = [rng.integers(0, 256, int(rng.integers(0, 150)), dtype=np.uint8).tobytes() for _ in range(k)]
+            leaves += new
+            root, size = a.append(new)
+            assert size == len(leaves) and root == OM.root(leaves), (trial, step, len(leaves))
+        st = a.save()                                       # checkpoint / resume
+        b = Auditor(ctx)
+        b.load(st)
+        more = [b"resume-%d" % i for i in range(37)]
+        assert b.append(more) == a.append(more) == (OM.root(leaves + more), len(leaves) + 37)
+        a.close(); b.close()
+
+
+def test_merkle_fold_of_aligned_shard_roots(ctx):
+    from agentfield_b200 import Auditor, fold_roots, shard
+    rng = np.random.default_rng(0xAF14)
+    for n in (8, 1000, 4096, 5000):
+        leaves = [rng.integers(0, 256, 96, dtype=np.uint8).tobytes() for _ in range(n)]
+        full = OM.root(leaves)
+        for world in (2, 8):
+            roots = []
+            for r in range(world):
+                lo, hi = shard.merkle_shard_range(n, r, world)
+                if hi > lo:
+                    a = Auditor(ctx)
+                    roots.append(a.append(leaves[lo:hi])[0])
+                    a.close()
+            assert fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx) == full, (n, world)
+
+
+# ----------------------------------------------------------------------------- device-pointer (resident) variants
+def test_device_resident_variants_equal_host_variants(ctx):
+    import torch
+    rng = np.random.default_rng(0xAF21)
+    n = 2048
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, (n, 512), dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * 512
+    dev = torch.device("cuda", 0)
+    d_seeds = torch.from_numpy(seeds).to(dev)
+    d_msgs = torch.from_numpy(msgs.reshape(-1)).to(dev)
+    d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_pks = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_dig = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    ctx.sign_dev(d_seeds, d_msgs, d_off, n, d_sigs)
+    d_exp = torch.empty((n, 96), dtype=torch.uint8, device=dev)
+    ctx.expand_dev(d_seeds, n, d_exp)
+    d_pks.copy_(d_exp[:, 64:])
+    ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)
+    ctx.sha256_dev(d_msgs, d_off, n, d_dig)
+    torch.cuda.synchronize()
+    sigs = ctx.sign_packed(seeds, msgs.reshape(-1), off)
+    assert (d_sigs.cpu().numpy() == sigs).all() and d_ok.cpu().numpy().all()
+    assert (d_dig.cpu().numpy() == CO.sha256_batch(msgs.reshape(-1), off, 4)).all()
+    d_sigs2 = torch.empty_like(d_sigs)
+    ctx.sign_expanded_dev(d_exp, None, d_msgs, d_off, n, d_sigs2)
+    torch.cuda.synchronize()
+    assert torch.equal(d_sigs, d_sigs2)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json sizes: properties
+def test_full_size_verify_properties_config2(ctx):
+    """cfg2 (1 M x 512 B, K = 1024 keys, 1 % corrupted): sign->verify round trip at full size; the ok-bitmap must equal
+    the corruption pattern exactly, and a 20 000-item sample must equal the oracle item by item."""
+    import torch
+    n, K = 1_000_000, 1024
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xAF02)
+    d_msgs = torch.randint(0, 256, (n, 512), dtype=torch.uint8, device=dev, generator=g)
+    d_kseeds = torch.randint(0, 256, (K, 32), dtype=torch.uint8, device=dev, generator=g)
+    d_exp = torch.empty((K, 96), dtype=torch.uint8, device=dev)
+    ctx.expand_dev(d_kseeds, K, d_exp)
+    d_ki = (torch.arange(n, device=dev) % K).to(torch.int32)
+    d_off = (torch.arange(n + 1, device=dev, dtype=torch.int64) * 512)
+    d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    ctx.sign_expanded_dev(d_exp, d_ki, d_msgs.view(-1), d_off, n, d_sigs)
+    d_pks = d_exp[:, 64:][d_ki.long()].contiguous()
+    idx = torch.arange(n, device=dev)
+    flip_msg = idx % 100 == 0
+    flip_s = idx % 100 == 50
+    bitpos = (idx // 100) % 4096
+    rows, cols = idx[flip_msg], bitpos[flip_msg] // 8
+    d_msgs[rows, cols] = d_msgs[rows, cols] ^ (1 << (bitpos[flip_msg] % 8)).to(torch.uint8)
+    srows = idx[flip_s]
+    d_sigs[srows, 33] = d_sigs[srows, 33] ^ 0x08
+    d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
+    ctx.verify_dev(d_pks, d_sigs, d_msgs.view(-1), d_off, n, d_ok)
+    torch.cuda.synchronize()
+    expect = (~(flip_msg | flip_s)).to(torch.uint8)
+    assert torch.equal(d_ok, expect)
+    assert int(d_ok.sum()) == n - 2 * (n // 100)
+    # oracle sample
+    m = 20_000
+    pk_h, sg_h, ms_h = d_pks[:m].cpu().numpy(), d_sigs[:m].cpu().numpy(), d_msgs[:m].cpu().numpy()
+    off_h = np.arange(m + 1, dtype=np.uint64) * 512
+    assert (CO.ed25519_verify_batch(pk_h, sg_h, ms_h.reshape(-1), off_h, 8) == d_ok[:m].cpu().numpy()).all()
+
+
+def test_full_size_hmac_properties_config3(ctx):
+    """cfg3 (10 M x 256 B bodies, 32 B per-message keys), processed resident in 2 M slices: a sampled slice equals the
+    oracle; tags are a deterministic function of (key, body) (same inputs twice -> same tags; one flipped bit -> new tag)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xAF03)
+    per, total = 2_000_000, 10_000_000
+    d_off = torch.arange(per + 1, device=dev, dtype=torch.int64) * 256
+    d_koff = (torch.arange(per + 1, device=dev, dtype=torch.int64) * 32).to(torch.int32)
+    xor_all = torch.zeros(32, dtype=torch.uint8, device=dev)
+    for sl in range(total // per):
+        d_bodies = torch.randint(0, 256, (per, 256), dtype=torch.uint8, device=dev, generator=g)
+        d_keys = torch.randint(0, 256, (per, 32), dtype=torch.uint8, device=dev, generator=g)
+        d_tags = torch.empty((per, 32), dtype=torch.uint8, device=dev)
+        ctx.hmac_sha256_dev(d_keys.view(-1), d_koff, d_bodies.view(-1), d_off, per, d_tags)
+        if sl == 0:
+            m = 30_000
+            exp = CO.hmac_sha256_batch(d_keys[:m].cpu().numpy().reshape(-1), np.arange(m + 1, dtype=np.uint32) * 32,
+                                       d_bodies[:m].cpu().numpy().reshape(-1), np.arange(m + 1, dtype=np.uint64) * 256, 8)
+            assert (d_tags[:m].cpu().numpy() == exp).all()
+            d_tags2 = torch.empty_like(d_tags)
+            ctx.hmac_sha256_dev(d_keys.view(-1), d_koff, d_bodies.view(-1), d_off, per, d_tags2)
+            assert torch.equal(d_tags, d_tags2)
+            d_bodies[::1000, 255] ^= 1
+            ctx.hmac_sha256_dev(d_keys.view(-1), d_koff, d_bodies.view(-1), d_off, per, d_tags2)
+            diff = (d_tags != d_tags2).any(dim=1)
+            assert int(diff.sum()) == len(range(0, per, 1000)) and bool(diff[::1000].all())
+        xor_all ^= torch.from_numpy(np.bitwise_xor.reduce(d_tags.cpu().numpy(), axis=0)).to(dev)
+    torch.cuda.synchronize()
+    assert xor_all.cpu().numpy().any()
+
+
+def test_full_size_merkle_config4_single_gpu(ctx):
+    """cfg4 shape on one GPU: 2^20 and a non-power-of-two leaf count; root == oracle root over the same leaf hashes;
+    8 aligned shard roots fold to the same root."""
+    import torch
+    from agentfield_b200 import Auditor, fold_roots, shard
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xAF04)
+    for n in (1 << 20, 1_000_003):
+        d_leaves = torch.randint(0, 256, (n, 96), dtype=torch.uint8, device=dev, generator=g)
+        d_off = torch.arange(n + 1, device=dev, dtype=torch.int64) * 96
+        a = Auditor(ctx)
+        a.append_dev(d_leaves.view(-1), d_off, n)
+        root, size = a.root()
+        assert size == n
+        d_lh = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+        ctx.merkle_leaf_hashes_dev(d_leaves.view(-1), d_off, n, d_lh)
+        torch.cuda.synchronize()
+        lh = d_lh.cpu().numpy()
+        assert lh[5].tobytes() == OM.leaf_hash(d_leaves[5].cpu().numpy().tobytes())
+        assert CO.merkle_root_from_hashes(lh) == root
+        roots = []
+        for r in range(8):
+            lo, hi = shard.merkle_shard_range(n, r, 8)
+            b = Auditor(ctx)
+            b.append_hashes_dev(d_lh[lo:hi], hi - lo)
+            roots.append(b.root()[0])
+            b.close()
+        assert fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx) == root
+        a.close()

@@ -1,0 +1,107 @@
+"""Host-side logic, no GPU: packing, Go-mirrored argument checks, shard partitions, and the N>1 Merkle
+exchange step over torch.distributed `gloo` (world_size 2) with the oracle standing in for the device hashing."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import merkle as M
+
+
+def test_pack_layout():
+    from agentfield_b200 import pack, pack32
+    buf, off = pack([b"ab", b"", b"cde"])
+    assert off.dtype == np.uint64 and off.tolist() == [0, 2, 2, 5] and bytes(buf[:5]) == b"abcde"
+    buf, off = pack([])
+    assert off.tolist() == [0]
+    kb, ko = pack32([b"k1", b"key2"])
+    assert ko.dtype == np.uint32 and ko.tolist() == [0, 2, 6]
+
+
+def test_go_mirrored_argument_errors():
+    """ed25519.Verify panics on a bad public-key length, NewKeyFromSeed on a bad seed length — before any packing
+    (so these raise even without a GPU)."""
+    from agentfield_b200 import Signer, Verifier
+
+    class _NoCtx:
+        pass
+    v, s = Verifier(ctx=_NoCtx()), Signer(ctx=_NoCtx())
+    with pytest.raises(ValueError, match="bad public key length"):
+        v.verify_batch([b"\x00" * 31], [b"m"], [b"\x00" * 64])
+    with pytest.raises(ValueError, match="bad seed length"):
+        s.sign_batch([b"\x00" * 33], [b"m"])
+    with pytest.raises(ValueError):
+        v.verify_batch([b"\x00" * 32], [b"m", b"n"], [b"\x00" * 64])
+    assert v.verify_batch([], [], []) == []
+
+
+def test_shard_partitions():
+    from agentfield_b200 import shard
+    for n in (0, 1, 7, 8, 1000, 4_000_000, 1 << 22):
+        for world in (1, 2, 4, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = shard.shard_range(n, r, world)
+                cover.append((lo, hi))
+            assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+            b = shard.merkle_block(n, world)
+            assert b & (b - 1) == 0 and b * world >= n and (b == 1 or (b // 2) * world < n)
+            mcover = [shard.merkle_shard_range(n, r, world) for r in range(world)]
+            assert mcover[0][0] == 0 and mcover[-1][1] == n and all(lo % b == 0 or lo == n for lo, _ in mcover)
+            assert sorted(i for r in range(world) for i in shard.round_robin_indices(min(n, 50), r, world)) == list(range(min(n, 50)))
+
+
+def test_aligned_shard_roots_fold_to_the_global_root():
+    """Why shards must be contiguous and 2^k-aligned: MTH over the per-shard roots == MTH over all leaves."""
+    from agentfield_b200 import shard
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 8, 100, 1000, 1025):
+        hs = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(n)]
+        full = M.root_from_leaf_hashes(hs)
+        for world in (1, 2, 4, 8):
+            roots = []
+            for r in range(world):
+                lo, hi = shard.merkle_shard_range(n, r, world)
+                if hi > lo:
+                    roots.append(M.root_from_leaf_hashes(hs[lo:hi]))
+            assert M.root_from_leaf_hashes(roots) == full, (n, world)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    from agentfield_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0xAF04)
+    leaves = [rng.integers(0, 256, 96, dtype=np.uint8).tobytes() for _ in range(n)]
+    lo, hi = shard.merkle_shard_range(n, rank, world)
+    local = M.root(leaves[lo:hi]) if hi > lo else None          # oracle stands in for the device hashing here
+    roots = shard.allgather_roots(local)
+    folded = M.root_from_leaf_hashes([r for r in roots if r is not None])
+    q.put((rank, folded.hex(), M.root(leaves).hex()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 1000])
+def test_merkle_exchange_step_world2_gloo(n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert len(res) == 2 and all(f == full for _, f, full in res) and res[0][1] == res[1][1]

@@ -1,0 +1,100 @@
+"""The kernel logic (agentfield_b200/csrc/*.cuh), compiled for the CPU by tests/hostsim (TEST-ONLY; portable code
+paths), against the oracle.  Catches arithmetic / padding / layout mistakes before GPU time is spent; the
+inline-PTX paths are checked on the device by afc_selftest (tests/test_gpu_parity.py)."""
+import ctypes as C
+import hashlib
+import hmac
+
+import numpy as np
+
+from conftest import golden
+from oracle import c_oracle as CO, go_ed25519 as G, merkle as M
+
+
+def _b(n):
+    return (C.c_uint8 * n)()
+
+
+def _placed(raw, al):
+    """Copy raw into a 16B-aligned scratch at byte offset al; returns (keepalive, pointer)."""
+    base = np.zeros(len(raw) + 64, dtype=np.uint8)
+    a0 = (-base.ctypes.data) % 16
+    base[a0 + al:a0 + al + len(raw)] = np.frombuffer(raw, dtype=np.uint8) if raw else []
+    return base, C.cast(base.ctypes.data + a0 + al, C.POINTER(C.c_uint8))
+
+
+def test_hash_padding_and_alignment(hostsim):
+    rng = np.random.default_rng(5)
+    for n in list(range(0, 140)) + [255, 256, 257, 511, 512, 513, 1300]:
+        for al in (0, 1, 2, 3):
+            m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            keep, p = _placed(m, al)
+            o = _b(32); hostsim.hs_sha256(p, C.c_uint64(n), o)
+            assert bytes(o) == hashlib.sha256(m).digest(), (n, al)
+            o = _b(32); hostsim.hs_merkle_leaf(p, C.c_uint64(n), o)
+            assert bytes(o) == M.leaf_hash(m), (n, al)
+            for kl in (0, 5, 32, 64, 65, 131):
+                k = rng.integers(0, 256, kl, dtype=np.uint8).tobytes()
+                o = _b(32); hostsim.hs_hmac_sha256(k, C.c_uint32(kl), p, C.c_uint64(n), o)
+                assert bytes(o) == hmac.new(k, m, hashlib.sha256).digest(), (n, al, kl)
+            pre = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+            o = _b(64); hostsim.hs_sha512_pre64(pre, p, C.c_uint64(n), o)
+            assert bytes(o) == hashlib.sha512(pre + m).digest(), (n, al)
+            o = _b(64); hostsim.hs_sha512_pre32(pre[:32], p, C.c_uint64(n), o)
+            assert bytes(o) == hashlib.sha512(pre[:32] + m).digest(), (n, al)
+    l, r = bytes(range(32)), bytes(range(32, 64))
+    o = _b(32); hostsim.hs_merkle_node(l, r, o)
+    assert bytes(o) == M.node_hash(l, r)
+
+
+def test_scalar_arithmetic(hostsim):
+    rng = np.random.default_rng(6)
+    L = G.L
+    specials = [b"\xff" * 64, bytes(64)] + [int(L * k + d).to_bytes(64, "little") for k in (1, 2, 2**250) for d in (-1, 0, 1)]
+    for i in range(1500):
+        x = specials[i] if i < len(specials) else rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        o = _b(32); hostsim.hs_sc_reduce512(x, o)
+        assert int.from_bytes(bytes(o), "little") == int.from_bytes(x, "little") % L
+        a, b, c = (rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(3))
+        o = _b(32); hostsim.hs_sc_muladd(a, b, c, o)
+        assert int.from_bytes(bytes(o), "little") == (int.from_bytes(a, "little") * int.from_bytes(b, "little") + int.from_bytes(c, "little")) % L
+
+
+def test_field_arithmetic(hostsim):
+    P = G.P
+    rng = np.random.default_rng(8)
+    edge = [0, 1, 2, 19, 37, 38, P - 1, P, P + 1, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**256 - 39, 2**256 - 37, 2**32 - 1, 2**64 - 1]
+    vals = edge + [int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") for _ in range(200)]
+
+    def op(code, x, y=0):
+        o = _b(32); hostsim.hs_fe_op(code, int(x).to_bytes(32, "little"), int(y).to_bytes(32, "little"), o)
+        return int.from_bytes(bytes(o), "little")
+
+    for x in vals[:30]:
+        for y in vals[:30]:
+            assert op(0, x, y) == x * y % P and op(2, x, y) == (x + y) % P and op(3, x, y) == (x - y) % P
+        assert op(1, x) == x * x % P and op(5, x) == x % P
+        if x % P:
+            assert op(4, x) == pow(x, P - 2, P)
+    for x, y in zip(vals[17:], reversed(vals[17:])):
+        assert op(0, x, y) == x * y % P and op(1, x) == x * x % P and op(2, x, y) == (x + y) % P and op(3, x, y) == (x - y) % P
+
+
+def test_ed25519_kernel_logic_vs_golden_and_oracle(hostsim):
+    for e in golden("rfc8032.json"):
+        seed, pk, msg, sig = (bytes.fromhex(e[k]) for k in ("seed", "pk", "msg", "sig"))
+        o = _b(32); hostsim.hs_pubkey(seed, o); assert bytes(o) == pk, e["name"]
+        o = _b(64); hostsim.hs_sign(seed, msg, C.c_uint64(len(msg)), o); assert bytes(o) == sig, e["name"]
+        assert hostsim.hs_verify(pk, msg, C.c_uint64(len(msg)), sig) == 1
+    for e in golden("ed25519_edge.json"):
+        pk, msg, sig = (bytes.fromhex(e[k]) for k in ("pk", "msg", "sig"))
+        assert hostsim.hs_verify(pk, msg, C.c_uint64(len(msg)), sig) == int(e["valid"]), e["name"]
+    rng = np.random.default_rng(10)
+    for i in range(150):
+        sd = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        m = rng.integers(0, 256, (i * 7) % 700, dtype=np.uint8).tobytes()
+        s, pk = CO.sign(sd, m), CO.pubkey(sd)
+        o = _b(64); hostsim.hs_sign(sd, m, C.c_uint64(len(m)), o); assert bytes(o) == s
+        assert hostsim.hs_verify(pk, m, C.c_uint64(len(m)), s) == 1
+        bs = bytearray(s); bs[i % 64] ^= 1 << (i % 8)
+        assert hostsim.hs_verify(pk, m, C.c_uint64(len(m)), bytes(bs)) == 0

@@ -1,0 +1,151 @@
+"""The oracle against the golden vectors (published KATs) and against two independent libraries.
+No GPU.  This is what pins the checker before it is trusted (prompt §③)."""
+import hashlib
+import hmac
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import c_oracle as CO, go_ed25519 as G, go_hash as H, merkle as M
+
+
+@pytest.mark.parametrize("impl", ["python", "c"])
+def test_rfc8032_vectors(impl):
+    for e in golden("rfc8032.json"):
+        seed, pk, msg, sig = (bytes.fromhex(e[k]) for k in ("seed", "pk", "msg", "sig"))
+        if impl == "python":
+            assert G.public_key(seed) == pk, e["name"]
+            assert G.sign(seed, msg) == sig, e["name"]
+            assert G.verify(pk, msg, sig), e["name"]
+        else:
+            assert CO.pubkey(seed) == pk, e["name"]
+            assert CO.sign(seed, msg) == sig, e["name"]
+            assert CO.verify(pk, msg, sig), e["name"]
+            assert not CO.verify(pk, msg + b"x", sig), e["name"]
+
+
+@pytest.mark.parametrize("impl", ["python", "c"])
+def test_ed25519_edge_set_go_rules(impl):
+    """Go's accept/reject rules (row E2): S canonical, sig[63]&0xE0, non-canonical / small-order A, R bytes."""
+    edge = golden("ed25519_edge.json")
+    assert sum(e["valid"] for e in edge) >= 10 and sum(not e["valid"] for e in edge) >= 30
+    for e in edge:
+        pk, msg, sig = (bytes.fromhex(e[k]) for k in ("pk", "msg", "sig"))
+        got = G.verify(pk, msg, sig) if impl == "python" else CO.verify(pk, msg, sig)
+        assert got == e["valid"], e["name"]
+
+
+def test_go_panics_on_bad_public_key_length():
+    with pytest.raises(ValueError):
+        G.verify(b"\x01" * 31, b"", b"\x00" * 64)
+    with pytest.raises(ValueError):
+        CO.verify(b"\x01" * 33, b"", b"\x00" * 64)
+    assert G.verify(b"\x01" * 32, b"", b"\x00" * 63) is False      # bad signature length is just false
+
+
+def test_c_oracle_matches_openssl_and_python_on_random_inputs():
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    rng = np.random.default_rng(1234)
+    for i in range(120):
+        seed = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        msg = rng.integers(0, 256, int(rng.integers(0, 1500)), dtype=np.uint8).tobytes()
+        sk = Ed25519PrivateKey.from_private_bytes(seed)
+        sig = sk.sign(msg)
+        pk = sk.public_key().public_bytes_raw()
+        assert CO.pubkey(seed) == pk and CO.sign(seed, msg) == sig
+        if i < 25:
+            assert G.sign(seed, msg) == sig
+        bad = bytearray(sig)
+        bad[i % 64] ^= 1 << (i % 8)
+        assert CO.verify(pk, msg, sig) and not CO.verify(pk, msg, bytes(bad))
+
+
+def test_c_oracle_batch_equals_openssl_batch():
+    rng = np.random.default_rng(99)
+    n = 600
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    lens = rng.integers(0, 700, n)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    buf = rng.integers(0, 256, int(off[-1]) + 1, dtype=np.uint8)
+    sigs = CO.ed25519_sign_batch(seeds, buf, off, 4)
+    assert (sigs == CO.ed25519_sign_batch(seeds, buf, off, 4, impl="ossl")).all()
+    pks = CO.ed25519_pubkey_batch(seeds, 4)
+    sigs[::5, 40] ^= 2
+    ok = CO.ed25519_verify_batch(pks, sigs, buf, off, 4)
+    assert (ok == CO.ed25519_verify_batch(pks, sigs, buf, off, 4, impl="ossl")).all()
+    assert ok.sum() == n - len(range(0, n, 5))
+    keys = rng.integers(0, 256, n * 40, dtype=np.uint8)
+    koff = (np.arange(n + 1) * 40).astype(np.uint32)
+    assert (CO.hmac_sha256_batch(keys, koff, buf, off, 4) == CO.hmac_sha256_batch(keys, koff, buf, off, 4, impl="ossl")).all()
+    assert (CO.sha256_batch(buf, off, 4) == CO.sha256_batch(buf, off, 4, impl="ossl")).all()
+
+
+def test_fips180_vectors():
+    for e in golden("fips180.json"):
+        msg = bytes.fromhex(e["repeat"]) * e["count"] if "repeat" in e else bytes.fromhex(e["msg"])
+        f = CO.sha256 if e["alg"] == "sha256" else CO.sha512
+        assert f(msg).hex() == e["digest"], e["source"]
+        assert getattr(hashlib, e["alg"])(msg).hexdigest() == e["digest"]
+
+
+def test_rfc4231_vectors():
+    for e in golden("rfc4231.json"):
+        key, msg = bytes.fromhex(e["key"]), bytes.fromhex(e["msg"])
+        assert CO.hmac_sha256(key, msg).hex() == e["tag"], e["name"]
+        assert H.hmac_sha256(key, msg).hex() == e["tag"], e["name"]
+        if "published_prefix" in e:
+            assert e["tag"].startswith(e["published_prefix"])
+        if "header" in e:
+            assert H.webhook_signature(key.decode(), msg) == e["header"] == "sha256=" + e["tag"]
+
+
+def test_rfc6962_vectors():
+    g = golden("rfc6962.json")
+    leaves = [bytes.fromhex(x) for x in g["leaves"]]
+    assert M.root([]).hex() == g["empty_root"]
+    for n in range(1, 9):
+        assert M.root(leaves[:n]).hex() == g["roots"][n - 1]
+        assert M.root_recursive(leaves[:n]).hex() == g["roots"][n - 1]
+        hs = np.frombuffer(b"".join(M.leaf_hash(x) for x in leaves[:n]), dtype=np.uint8).reshape(-1, 32)
+        assert CO.merkle_root_from_hashes(hs).hex() == g["roots"][n - 1]
+    for s in g["synthetic"]:
+        if s["leaves"] is not None:
+            ls = [bytes.fromhex(x) for x in s["leaves"]]
+            assert M.root(ls).hex() == s["root"]
+            buf = np.frombuffer(b"".join(ls), dtype=np.uint8)
+            off = (np.arange(len(ls) + 1) * s["leaf_len"]).astype(np.uint64)
+            assert CO.merkle_root(buf, off, 2).hex() == s["root"]
+
+
+def test_merkle_frontier_and_inclusion_proofs():
+    rng = np.random.default_rng(7)
+    hs = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(77)]
+    for n in (1, 2, 3, 5, 8, 13, 64, 77):
+        r = M.root_from_leaf_hashes(hs[:n])
+        assert M.root_from_frontier(M.frontier(hs[:n])) == r
+        for m in {0, n // 2, n - 1}:
+            assert M.verify_inclusion(hs[m], m, n, M.inclusion_proof(hs[:n], m), r)
+            assert not M.verify_inclusion(hs[(m + 1) % len(hs)], m, n, M.inclusion_proof(hs[:n], m), r) or n == 1 and False
+
+
+def test_reference_flow_vectors():
+    """Key derivation, did:key, hashData and a VC-shaped canonical message (did_service.go:515-536,
+    vc_service.go:434-515)."""
+    g = golden("reference_flow.json")
+    master = bytes.fromhex(g["master_seed"])
+    for d in g["derivations"]:
+        seed = H.derive_seed(master, d["path"])
+        assert seed.hex() == d["seed"] == CO.sha256(master + d["path"].encode()).hex()
+        assert CO.pubkey(seed).hex() == d["pk"]
+        assert H.did_key(bytes.fromhex(d["pk"])) == d["did"] and len(d["did"]) == 55
+    for h in g["hash_data"]:
+        payload = None if h["payload"] is None else bytes.fromhex(h["payload"])
+        enc = H.marshal_data_or_null(payload)
+        assert enc.hex() == h["marshalled"] and H.hash_data(enc) == h["hash"] and len(h["hash"]) == 43
+    vc = g["vc"]
+    msg = vc["canonical"].encode()
+    assert CO.sign(bytes.fromhex(vc["seed"]), msg).hex() == vc["sig"]
+    assert CO.verify(bytes.fromhex(vc["pk"]), msg, bytes.fromhex(vc["sig"]))
+    assert H.b64url_nopad(bytes.fromhex(vc["sig"])) == vc["proofValue"]
