@@ -472,9 +472,29 @@ AFC_HD void fe_sq(fe& h, const fe& f) {
     fe_fold16(h, t);
 }
 
-AFC_HD void fe_sqn(fe& h, const fe& f, int n) {
-    fe_sq(h, f);
-    for (int i = 1; i < n; i++) fe_sq(h, h);
+// Field-multiplication policy.  FeInline expands the ~100-instruction multiply at every call site (fastest per call,
+// but the verify loop then spans ~80 KB of SASS and misses the instruction cache); FeCall routes through ONE
+// out-of-line copy with operands passed in registers, which keeps the whole double-scalar loop I-cache resident.
+struct FeInline {
+    static AFC_HDM void mul(fe& h, const fe& f, const fe& g) { fe_mul(h, f, g); }
+    static AFC_HDM void sq(fe& h, const fe& f) { fe_sq(h, f); }
+};
+#if !defined(AFC_HOSTSIM)
+static __device__ __noinline__ fe fe_mul_call(fe f, fe g) { fe h; fe_mul(h, f, g); return h; }
+static __device__ __noinline__ fe fe_sq_call(fe f) { fe h; fe_sq(h, f); return h; }
+struct FeCall {
+    static AFC_HDM void mul(fe& h, const fe& f, const fe& g) { h = fe_mul_call(f, g); }
+    static AFC_HDM void sq(fe& h, const fe& f) { h = fe_sq_call(f); }
+};
+#endif
+
+
+
+template <class F = FeInline>
+AFC_HD void fe_sqn_t(fe& h, const fe& f, int n) {
+    F::sq(h, f);
+#pragma unroll 1
+    for (int i = 1; i < n; i++) F::sq(h, h);
 }
 
 // ---------------------------------------------------------------------------------- encode / decode
@@ -516,34 +536,37 @@ AFC_HD int fe_equal(const fe& a, const fe& b) { fe d; fe_sub(d, a, b); return fe
 
 // ---------------------------------------------------------------------------------- exponentiations
 // z^(2^250-1) and z^11 (shared prefix of the inversion and square-root chains)
+template <class F = FeInline>
 AFC_HD void fe_pow_2_250_m1(fe& out, fe& z11, const fe& z) {
     fe t0, t1, t2, t3;
-    fe_sq(t0, z);                               // 2
-    fe_sqn(t1, t0, 2);                          // 8
-    fe_mul(t1, z, t1);                          // 9
-    fe_mul(t0, t0, t1);                         // 11
+    F::sq(t0, z);                               // 2
+    fe_sqn_t<F>(t1, t0, 2);                          // 8
+    F::mul(t1, z, t1);                          // 9
+    F::mul(t0, t0, t1);                         // 11
     fe_copy(z11, t0);
-    fe_sq(t2, t0);                              // 22
-    fe_mul(t1, t1, t2);                         // 2^5-1
-    fe_sqn(t2, t1, 5);   fe_mul(t1, t2, t1);    // 2^10-1
-    fe_sqn(t2, t1, 10);  fe_mul(t2, t2, t1);    // 2^20-1
-    fe_sqn(t3, t2, 20);  fe_mul(t2, t3, t2);    // 2^40-1
-    fe_sqn(t2, t2, 10);  fe_mul(t1, t2, t1);    // 2^50-1
-    fe_sqn(t2, t1, 50);  fe_mul(t2, t2, t1);    // 2^100-1
-    fe_sqn(t3, t2, 100); fe_mul(t2, t3, t2);    // 2^200-1
-    fe_sqn(t2, t2, 50);  fe_mul(out, t2, t1);   // 2^250-1
+    F::sq(t2, t0);                              // 22
+    F::mul(t1, t1, t2);                         // 2^5-1
+    fe_sqn_t<F>(t2, t1, 5);   F::mul(t1, t2, t1);    // 2^10-1
+    fe_sqn_t<F>(t2, t1, 10);  F::mul(t2, t2, t1);    // 2^20-1
+    fe_sqn_t<F>(t3, t2, 20);  F::mul(t2, t3, t2);    // 2^40-1
+    fe_sqn_t<F>(t2, t2, 10);  F::mul(t1, t2, t1);    // 2^50-1
+    fe_sqn_t<F>(t2, t1, 50);  F::mul(t2, t2, t1);    // 2^100-1
+    fe_sqn_t<F>(t3, t2, 100); F::mul(t2, t3, t2);    // 2^200-1
+    fe_sqn_t<F>(t2, t2, 50);  F::mul(out, t2, t1);   // 2^250-1
 }
+template <class F = FeInline>
 AFC_HD void fe_invert(fe& out, const fe& z) {
     fe t, z11;
-    fe_pow_2_250_m1(t, z11, z);
-    fe_sqn(t, t, 5);
-    fe_mul(out, t, z11);                        // z^(2^255-21) = z^(p-2)
+    fe_pow_2_250_m1<F>(t, z11, z);
+    fe_sqn_t<F>(t, t, 5);
+    F::mul(out, t, z11);                        // z^(2^255-21) = z^(p-2)
 }
+template <class F = FeInline>
 AFC_HD void fe_pow22523(fe& out, const fe& z) {
     fe t, z11;
-    fe_pow_2_250_m1(t, z11, z);
-    fe_sqn(t, t, 2);
-    fe_mul(out, t, z);                          // z^(2^252-3) = z^((p-5)/8)
+    fe_pow_2_250_m1<F>(t, z11, z);
+    fe_sqn_t<F>(t, t, 2);
+    F::mul(out, t, z);                          // z^(2^252-3) = z^((p-5)/8)
 }
 
 }  // namespace afc

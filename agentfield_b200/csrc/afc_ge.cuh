@@ -28,20 +28,25 @@ AFC_HD void fe_const(fe& h, const uint32_t* c) {
     for (int i = 0; i < 8; i++) h.v[i] = c[i];
 }
 
+
 AFC_HD void ge_p3_0(ge_p3& h) { fe_0(h.X); fe_1(h.Y); fe_1(h.Z); fe_0(h.T); }
-AFC_HD void ge_p1p1_to_p2(ge_p2& r, const ge_p1p1& p) { fe_mul(r.X, p.X, p.T); fe_mul(r.Y, p.Y, p.Z); fe_mul(r.Z, p.Z, p.T); }
+template <class F = FeInline>
+AFC_HD void ge_p1p1_to_p2(ge_p2& r, const ge_p1p1& p) { F::mul(r.X, p.X, p.T); F::mul(r.Y, p.Y, p.Z); F::mul(r.Z, p.Z, p.T); }
+template <class F = FeInline>
 AFC_HD void ge_p1p1_to_p3(ge_p3& r, const ge_p1p1& p) {
-    fe_mul(r.X, p.X, p.T); fe_mul(r.Y, p.Y, p.Z); fe_mul(r.Z, p.Z, p.T); fe_mul(r.T, p.X, p.Y);
+    F::mul(r.X, p.X, p.T); F::mul(r.Y, p.Y, p.Z); F::mul(r.Z, p.Z, p.T); F::mul(r.T, p.X, p.Y);
 }
+template <class F = FeInline>
 AFC_HD void ge_p3_to_cached(ge_cached& r, const ge_p3& p) {
     fe d2; fe_const(d2, AFC_D2_32);
-    fe_add(r.YpX, p.Y, p.X); fe_sub(r.YmX, p.Y, p.X); fe_copy(r.Z, p.Z); fe_mul(r.T2d, p.T, d2);
+    fe_add(r.YpX, p.Y, p.X); fe_sub(r.YmX, p.Y, p.X); fe_copy(r.Z, p.Z); F::mul(r.T2d, p.T, d2);
 }
 // r = 2 * (X:Y:Z)
+template <class F = FeInline>
 AFC_HD void ge_dbl(ge_p1p1& r, const fe& X, const fe& Y, const fe& Z) {
     fe xx, yy, b, a;
-    fe_sq(xx, X); fe_sq(yy, Y); fe_sq(b, Z); fe_dbl(b, b);
-    fe_add(a, X, Y); fe_sq(a, a);
+    F::sq(xx, X); F::sq(yy, Y); F::sq(b, Z); fe_dbl(b, b);
+    fe_add(a, X, Y); F::sq(a, a);
     fe_add(r.Y, yy, xx); fe_sub(r.Z, yy, xx); fe_sub(r.X, a, r.Y); fe_sub(r.T, b, r.Z);
 }
 AFC_HD void fe_select(fe& h, const fe& a, const fe& b, int pick_b) {
@@ -50,66 +55,71 @@ AFC_HD void fe_select(fe& h, const fe& a, const fe& b, int pick_b) {
     for (int i = 0; i < 8; i++) h.v[i] = (a.v[i] & ~m) | (b.v[i] & m);
 }
 // r = p + q (neg = 0) or p - q (neg = 1)
+template <class F = FeInline>
 AFC_HD void ge_addsub(ge_p1p1& r, const ge_p3& p, const ge_cached& q, int neg) {
     fe a, b, c, d, qa, qb;
     fe_select(qa, q.YpX, q.YmX, neg);
     fe_select(qb, q.YmX, q.YpX, neg);
     fe_add(a, p.Y, p.X); fe_sub(b, p.Y, p.X);
-    fe_mul(a, a, qa); fe_mul(b, b, qb); fe_mul(c, q.T2d, p.T); fe_mul(d, p.Z, q.Z); fe_dbl(d, d);
+    F::mul(a, a, qa); F::mul(b, b, qb); F::mul(c, q.T2d, p.T); F::mul(d, p.Z, q.Z); fe_dbl(d, d);
     fe_sub(r.X, a, b); fe_add(r.Y, a, b);
     fe dpc, dmc;
     fe_add(dpc, d, c); fe_sub(dmc, d, c);
     fe_select(r.Z, dpc, dmc, neg); fe_select(r.T, dmc, dpc, neg);
 }
 // mixed addition with an affine precomputed point
+template <class F = FeInline>
 AFC_HD void ge_maddsub(ge_p1p1& r, const ge_p3& p, const ge_precomp& q, int neg) {
     fe a, b, c, d, qa, qb;
     fe_select(qa, q.ypx, q.ymx, neg);
     fe_select(qb, q.ymx, q.ypx, neg);
     fe_add(a, p.Y, p.X); fe_sub(b, p.Y, p.X);
-    fe_mul(a, a, qa); fe_mul(b, b, qb); fe_mul(c, q.xy2d, p.T); fe_dbl(d, p.Z);
+    F::mul(a, a, qa); F::mul(b, b, qb); F::mul(c, q.xy2d, p.T); fe_dbl(d, p.Z);
     fe_sub(r.X, a, b); fe_add(r.Y, a, b);
     fe dpc, dmc;
     fe_add(dpc, d, c); fe_sub(dmc, d, c);
     fe_select(r.Z, dpc, dmc, neg); fe_select(r.T, dmc, dpc, neg);
 }
+template <class F = FeInline>
 AFC_HD void ge_p3_to_precomp(ge_precomp& r, const ge_p3& p) {
     fe zi, x, y, xy, d2;
     fe_const(d2, AFC_D2_32);
-    fe_invert(zi, p.Z); fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi);
-    fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); fe_mul(xy, x, y); fe_mul(r.xy2d, xy, d2);
+    fe_invert<F>(zi, p.Z); F::mul(x, p.X, zi); F::mul(y, p.Y, zi);
+    fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); F::mul(xy, x, y); F::mul(r.xy2d, xy, d2);
 }
 // canonical 32-byte encoding as little-endian words (Point.Bytes)
+template <class F = FeInline>
 AFC_HD void ge_encode(uint32_t* out, const fe& X, const fe& Y, const fe& Z) {
     fe zi, x, y;
-    fe_invert(zi, Z); fe_mul(x, X, zi); fe_mul(y, Y, zi);
+    fe_invert<F>(zi, Z); F::mul(x, X, zi); F::mul(y, Y, zi);
     fe_towords(out, y);
     out[7] |= (uint32_t)fe_isnegative(x) << 31;
 }
 // Point.SetBytes: 1 on success, 0 if the encoding is not on the curve.  Non-canonical y and
 // "x = 0 with sign bit" are accepted exactly as Go does.
+template <class F = FeInline>
 AFC_HD int ge_frombytes(ge_p3& h, const uint32_t* enc) {
     fe u, v, v3, vxx, one, dd, sm1;
     fe_1(one); fe_const(dd, AFC_D_32); fe_const(sm1, AFC_SQRTM1_32);
     fe_frombytes_words(h.Y, enc);
     fe_1(h.Z);
-    fe_sq(u, h.Y); fe_mul(v, u, dd);
+    F::sq(u, h.Y); F::mul(v, u, dd);
     fe_sub(u, u, one);                      // u = y^2 - 1
     fe_add(v, v, one);                      // v = d y^2 + 1
-    fe_sq(v3, v); fe_mul(v3, v3, v);        // v^3
-    fe_sq(h.X, v3); fe_mul(h.X, h.X, v); fe_mul(h.X, h.X, u);   // u v^7
-    fe_pow22523(h.X, h.X);
-    fe_mul(h.X, h.X, v3); fe_mul(h.X, h.X, u);                   // r = u v^3 (u v^7)^((p-5)/8)
-    fe_sq(vxx, h.X); fe_mul(vxx, vxx, v);                        // v r^2
+    F::sq(v3, v); F::mul(v3, v3, v);        // v^3
+    F::sq(h.X, v3); F::mul(h.X, h.X, v); F::mul(h.X, h.X, u);   // u v^7
+    fe_pow22523<F>(h.X, h.X);
+    F::mul(h.X, h.X, v3); F::mul(h.X, h.X, u);                   // r = u v^3 (u v^7)^((p-5)/8)
+    F::sq(vxx, h.X); F::mul(vxx, vxx, v);                        // v r^2
     int ok_pos = fe_equal(vxx, u);
     fe nu; fe_neg(nu, u);
     int ok_neg = fe_equal(vxx, nu);
-    fe xi; fe_mul(xi, h.X, sm1);
+    fe xi; F::mul(xi, h.X, sm1);
     fe_select(h.X, h.X, xi, ok_neg & !ok_pos);
     int flip = fe_isnegative(h.X) != (int)(enc[7] >> 31);
     fe nx; fe_neg(nx, h.X);
     fe_select(h.X, h.X, nx, flip);
-    fe_mul(h.T, h.X, h.Y);
+    F::mul(h.T, h.X, h.Y);
     return ok_pos | ok_neg;
 }
 
@@ -124,33 +134,36 @@ struct BaseTables {
 
 // Row i of the fixed-base table: row[j] = (j+1) * 16^i * B in affine precomputed form.  One thread per
 // row at afc_init (k_build_tables); row 0 doubles as the 8-entry table b8 used by verification.
+template <class F = FeInline>
 AFC_HD void ge_build_comb_row(ge_precomp* row, int i) {
     ge_p3 P, M;
-    fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); fe_mul(P.T, P.X, P.Y);
+    fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); F::mul(P.T, P.X, P.Y);
     ge_p1p1 t;
-    for (int k = 0; k < 4 * i; k++) { ge_dbl(t, P.X, P.Y, P.Z); ge_p1p1_to_p3(P, t); }
+    for (int k = 0; k < 4 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
     ge_cached c;
-    ge_p3_to_cached(c, P);
+    ge_p3_to_cached<F>(c, P);
     M = P;
     for (int j = 0; j < 8; j++) {
-        ge_p3_to_precomp(row[j], M);
-        ge_addsub(t, M, c, 0); ge_p1p1_to_p3(M, t);
+        ge_p3_to_precomp<F>(row[j], M);
+        ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
     }
 }
 
 // h = a * B for a reduced scalar a (< 2^253): 64 mixed additions, no doublings.
+template <class F = FeInline>
 AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* comb) {
     uint32_t t[8];
     sc_recode16(t, a);
     ge_p3_0(h);
+#pragma unroll 1
     for (int i = 0; i < 64; i++) {
         int d = sc_digit16(t, i);
         if (d != 0) {
             int neg = d < 0;
             int m = neg ? -d : d;
             ge_p1p1 r;
-            ge_maddsub(r, h, comb[i * 8 + (m - 1)], neg);
-            ge_p1p1_to_p3(h, r);
+            ge_maddsub<F>(r, h, comb[i * 8 + (m - 1)], neg);
+            ge_p1p1_to_p3<F>(h, r);
         }
     }
 }
@@ -158,52 +171,62 @@ AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* co
 // ---------------------------------------------------------------------------------- verify core
 // pk, sig: little-endian words of the given byte strings; k = SHA-512(R || A || M) mod L.
 // Returns 1 iff Go's ed25519.Verify would return true.
+template <class F = FeInline>
 AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const uint32_t* k, const ge_precomp* b8) {
     int ok = 1;
     if (sig[15] & 0xE0000000u) ok = 0;                 // sig[63] & 224 != 0
     if (!sc_is_canonical(sig + 8)) ok = 0;             // S >= L
     ge_p3 A;
-    if (!ge_frombytes(A, pk)) ok = 0;
+    if (!ge_frombytes<F>(A, pk)) ok = 0;
     fe_neg(A.X, A.X); fe_neg(A.T, A.T);                // -A
     ge_cached tab[8];                                  // (j+1)(-A)
-    ge_p3_to_cached(tab[0], A);
+    ge_p3_to_cached<F>(tab[0], A);
     {
         ge_p3 m; ge_p1p1 t;
-        ge_dbl(t, A.X, A.Y, A.Z); ge_p1p1_to_p3(m, t);  // 2(-A)
-        ge_p3_to_cached(tab[1], m);
+        ge_dbl<F>(t, A.X, A.Y, A.Z); ge_p1p1_to_p3<F>(m, t);  // 2(-A)
+        ge_p3_to_cached<F>(tab[1], m);
         for (int j = 2; j < 8; j++) {
-            ge_addsub(t, m, tab[0], 0); ge_p1p1_to_p3(m, t);
-            ge_p3_to_cached(tab[j], m);
+            ge_addsub<F>(t, m, tab[0], 0); ge_p1p1_to_p3<F>(m, t);
+            ge_p3_to_cached<F>(tab[j], m);
         }
     }
     uint32_t kt[8], st[8];
     sc_recode16(kt, k);
     sc_recode16(st, sig + 8);
-    ge_p3 r; ge_p3_0(r);
+    // Straus over one shared doubling chain.  The running point lives in P1xP1 form (t) between steps: it is completed
+    // to P3 (4 mul) only right before an addition needs T, and to P2 (3 mul) before doublings.
+    ge_p2 q;
     ge_p1p1 t;
+    fe_0(t.X); fe_1(t.Y); fe_1(t.Z); fe_1(t.T);            // identity
+#pragma unroll 1
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
-            ge_p2 q;
-            ge_dbl(t, r.X, r.Y, r.Z); ge_p1p1_to_p2(q, t);
-            ge_dbl(t, q.X, q.Y, q.Z); ge_p1p1_to_p2(q, t);
-            ge_dbl(t, q.X, q.Y, q.Z); ge_p1p1_to_p2(q, t);
-            ge_dbl(t, q.X, q.Y, q.Z); ge_p1p1_to_p3(r, t);
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) {
+                ge_p1p1_to_p2<F>(q, t);
+                ge_dbl<F>(t, q.X, q.Y, q.Z);
+            }
         }
         int dk = sc_digit16(kt, i);
         if (dk != 0) {
             int neg = dk < 0;
             int m = neg ? -dk : dk;
-            ge_addsub(t, r, tab[m - 1], neg); ge_p1p1_to_p3(r, t);
+            ge_p3 r;
+            ge_p1p1_to_p3<F>(r, t);
+            ge_addsub<F>(t, r, tab[m - 1], neg);
         }
         int ds = sc_digit16(st, i);
         if (ds != 0) {
             int neg = ds < 0;
             int m = neg ? -ds : ds;
-            ge_maddsub(t, r, b8[m - 1], neg); ge_p1p1_to_p3(r, t);
+            ge_p3 r;
+            ge_p1p1_to_p3<F>(r, t);
+            ge_maddsub<F>(t, r, b8[m - 1], neg);
         }
     }
+    ge_p1p1_to_p2<F>(q, t);
     uint32_t enc[8];
-    ge_encode(enc, r.X, r.Y, r.Z);
+    ge_encode<F>(enc, q.X, q.Y, q.Z);
     uint32_t diff = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) diff |= enc[i] ^ sig[i];
@@ -221,6 +244,7 @@ AFC_HD void ed25519_hram(uint32_t* k, const uint32_t* pk, const uint32_t* sig, c
 
 // ---------------------------------------------------------------------------------- key expansion / sign
 // NewKeyFromSeed: s = clamp(SHA-512(seed)[0:32]) (unreduced), prefix = SHA-512(seed)[32:64], A = [s]B.
+template <class F = FeInline>
 AFC_HD void ed25519_expand(uint32_t* s, uint32_t* prefix, uint32_t* pk, const uint32_t* seed, const ge_precomp* comb) {
     uint32_t dig[16];
     sha512_prefixed<8>(dig, seed, (const uint8_t*)0, 0);
@@ -232,18 +256,19 @@ AFC_HD void ed25519_expand(uint32_t* s, uint32_t* prefix, uint32_t* pk, const ui
     uint32_t sr[8];
     sc_reduce256(sr, s);
     ge_p3 A;
-    ge_scalarmult_base(A, sr, comb);
-    ge_encode(pk, A.X, A.Y, A.Z);
+    ge_scalarmult_base<F>(A, sr, comb);
+    ge_encode<F>(pk, A.X, A.Y, A.Z);
 }
 // Sign with an expanded key (s, prefix, pk)
+template <class F = FeInline>
 AFC_HD void ed25519_sign_expanded(uint32_t* sig, const uint32_t* s, const uint32_t* prefix, const uint32_t* pk,
                                    const uint8_t* msg, uint64_t len, const ge_precomp* comb) {
     uint32_t dig[16], r[8], k[8];
     sha512_prefixed<8>(dig, prefix, msg, len);
     sc_reduce512(r, dig);
     ge_p3 R;
-    ge_scalarmult_base(R, r, comb);
-    ge_encode(sig, R.X, R.Y, R.Z);
+    ge_scalarmult_base<F>(R, r, comb);
+    ge_encode<F>(sig, R.X, R.Y, R.Z);
     ed25519_hram(k, pk, sig, msg, len);
     sc_muladd(sig + 8, k, s, r);
 }

@@ -22,20 +22,32 @@ namespace afc {
 AFC_HD uint32_t ch32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (~x & z); }
 AFC_HD uint32_t maj32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (x & z) ^ (y & z); }
 
+// Out-of-line on the device: HMAC alone has five compression call sites; inlining each (~1.6k instructions) would
+// put >100 KB of SASS in one kernel and stall every warp on instruction fetch (ncu: stall_no_instruction).
+#if defined(AFC_HOSTSIM)
+#define AFC_OUTLINE static inline
+#else
+#define AFC_OUTLINE static __device__ __noinline__
+#endif
+
 // One compression: st += F(st, w[0..15]) — w is consumed (used as the rolling schedule window).
-AFC_HD void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+// Rounds are unrolled 16 at a time (4 trips): schedule indices stay compile-time, K comes from the constant bank.
+AFC_OUTLINE void sha256_compress(uint32_t* st, uint32_t* w) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 1
+    for (int r = 0; r < 64; r += 16) {
 #pragma unroll
-    for (int i = 0; i < 64; i++) {
-        if (i >= 16) {
-            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
-            uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-            uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        for (int j = 0; j < 16; j++) {
+            if (r > 0) {
+                uint32_t w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
+                uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
+            }
+            uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[r + j] + w[j];
+            uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         }
-        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[i] + w[i & 15];
-        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
@@ -174,19 +186,22 @@ AFC_HD void store_digest256(uint8_t* out, const uint32_t st[8]) {
 }
 
 // ---------------------------------------------------------------------------------- SHA-512
-AFC_HD void sha512_compress(uint64_t st[8], uint64_t w[16]) {
+AFC_OUTLINE void sha512_compress(uint64_t* st, uint64_t* w) {
     uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 1
+    for (int r = 0; r < 80; r += 16) {
 #pragma unroll
-    for (int i = 0; i < 80; i++) {
-        if (i >= 16) {
-            uint64_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
-            uint64_t s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
-            uint64_t s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
-            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        for (int j = 0; j < 16; j++) {
+            if (r > 0) {
+                uint64_t w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
+                uint64_t s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+                uint64_t s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+                w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
+            }
+            uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + AFC_K512[r + j] + w[j];
+            uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         }
-        uint64_t t1 = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + AFC_K512[i] + w[i & 15];
-        uint64_t t2 = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }

@@ -96,6 +96,7 @@ struct afc_merkle {
     uint8_t* d_root = nullptr;       // 32
     DevBuf lv[2], leaves, off;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;        // last device-side work enqueued on a caller's stream (orders _dev calls vs host calls)
     std::mutex mu;
 };
 
@@ -494,6 +495,8 @@ int afc_merkle_new(afc_ctx* ctx, afc_merkle** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_root, 32);
     if (e == cudaSuccess) e = cudaMemset(m->d_frontier, 0, 64 * 32);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(m->ev, m->stream);
     if (e != cudaSuccess) { set_err(ctx, e, "afc_merkle_new"); afc_merkle_free(m); return AFC_ECUDA; }
     *out = m;
     return AFC_OK;
@@ -502,6 +505,7 @@ void afc_merkle_free(afc_merkle* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    if (m->ev) cudaEventDestroy(m->ev);
     if (m->d_frontier) cudaFree(m->d_frontier);
     if (m->d_root) cudaFree(m->d_root);
     m->lv[0].release(); m->lv[1].release(); m->leaves.release(); m->off.release();
@@ -545,8 +549,11 @@ int afc_merkle_append_hashes_dev(afc_merkle* m, const uint8_t* d_hashes32, uint3
     afc_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(m->mu);
-    // the level buffers are reused across calls: a caller-supplied stream must be ordered after prior work
-    return merkle_append_hashes_locked(m, d_hashes32, n, (cudaStream_t)stream);
+    // the log state and level buffers are shared across calls: order this stream after whatever touched them last
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev, 0));
+    int rc = merkle_append_hashes_locked(m, d_hashes32, n, (cudaStream_t)stream);
+    CK(cudaEventRecord(m->ev, (cudaStream_t)stream));
+    return rc;
 }
 int afc_merkle_append_dev(afc_merkle* m, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, void* stream) {
     if (!m) return AFC_EINVAL;
@@ -555,9 +562,12 @@ int afc_merkle_append_dev(afc_merkle* m, const uint8_t* d_leaves, const uint64_t
     std::lock_guard<std::mutex> g(m->mu);
     if (n == 0) return AFC_OK;
     CallLog lc(ctx);
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev, 0));
     CK(m->lv[1].reserve((size_t)n * 32));
     CK(launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, m->lv[1].p, (cudaStream_t)stream, lc));
-    return merkle_append_hashes_locked(m, m->lv[1].p, n, (cudaStream_t)stream);
+    int rc = merkle_append_hashes_locked(m, m->lv[1].p, n, (cudaStream_t)stream);
+    CK(cudaEventRecord(m->ev, (cudaStream_t)stream));
+    return rc;
 }
 int afc_merkle_root_dev(afc_merkle* m, uint8_t* d_root32, void* stream) {
     if (!m || !d_root32) return AFC_EINVAL;
@@ -566,12 +576,15 @@ int afc_merkle_root_dev(afc_merkle* m, uint8_t* d_root32, void* stream) {
     std::lock_guard<std::mutex> g(m->mu);
     CallLog lc(ctx);
     if (!aligned16(d_root32)) return AFC_EINVAL;
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev, 0));
     CK(launch::merkle_root(m->d_frontier, m->size, d_root32, (cudaStream_t)stream, lc));
+    CK(cudaEventRecord(m->ev, (cudaStream_t)stream));
     return AFC_OK;
 }
 static int merkle_root_host_locked(afc_merkle* m, uint8_t root32[32], uint64_t* tree_size) {
     afc_ctx* ctx = m->ctx;
     CallLog lc(ctx);
+    CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     CK(launch::merkle_root(m->d_frontier, m->size, m->d_root, m->stream, lc));
     if (root32) CK(cudaMemcpyAsync(root32, m->d_root, 32, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -590,6 +603,7 @@ int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf
     afc_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     if (n) {
         uint64_t base = leaf_off[0], bytes = leaf_off[n] - base;
         if (bytes && !leaves) return AFC_EINVAL;
@@ -609,6 +623,7 @@ int afc_merkle_append_hashes(afc_merkle* m, const uint8_t* hashes32, uint32_t n,
     afc_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     if (n) {
         CK(m->lv[1].reserve((size_t)n * 32));
         CK(cudaMemcpyAsync(m->lv[1].p, hashes32, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
@@ -622,6 +637,7 @@ int afc_merkle_save(afc_merkle* m, uint8_t* state) {
     afc_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     CK(cudaStreamSynchronize(m->stream));
     memcpy(state, &m->size, 8);
     CK(cudaMemcpy(state + 8, m->d_frontier, 64 * 32, cudaMemcpyDeviceToHost));
@@ -633,6 +649,7 @@ int afc_merkle_load(afc_merkle* m, const uint8_t* state) {
     afc_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(m->mu);
+    CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     CK(cudaStreamSynchronize(m->stream));
     memcpy(&m->size, state, 8);
     CK(cudaMemcpy(m->d_frontier, state + 8, 64 * 32, cudaMemcpyHostToDevice));
@@ -793,7 +810,7 @@ int afc_microbench(afc_ctx* ctx, int which, uint32_t iters, double* ops_per_s, d
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     CK(e);
-    double per_thread = (which == 3 || which == 4) ? 1.0 : 2.0;   // fe probes do two ops per iteration
+    double per_thread = (which == 3 || which == 4) ? 1.0 : (which >= 10 ? 16.0 : 2.0);   // fe probes: 2 ops / iteration; pipe probes: 16 instr
     *ops_per_s = (double)blocks * threads * iters * per_thread / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
     return AFC_OK;

@@ -10,6 +10,8 @@
 //   k_ed_verify  R'_i = [S_i]B + [k_i](-A_i); ok_i = enc(R'_i) == R_i  (pure 32-bit IMAD/IADD3 work,
 //                ~2.9k field multiplications per credential — >99% of the time)
 // One credential per thread; fixed 4-bit windows keep all 32 lanes on one instruction stream.
+#include <cstdlib>
+
 #include "afc_launch.h"
 #include "afc_ge.cuh"
 
@@ -30,7 +32,7 @@ __device__ __forceinline__ void store_words8(uint8_t* p, const uint32_t* w) {
 
 __global__ void k_ed_build_tables(ge_precomp* comb) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 64) ge_build_comb_row(comb + 8 * i, i);
+    if (i < 64) ge_build_comb_row<FeCall>(comb + 8 * i, i);
 }
 
 __global__ void __launch_bounds__(ED_THREADS)
@@ -46,7 +48,10 @@ k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, con
     store_words8((uint8_t*)(k_out + 8ull * i), k);
 }
 
-__global__ void __launch_bounds__(ED_THREADS)
+// Variants (selected with AFC_VERIFY_VARIANT, default 1) differ only in how field multiplications are emitted and in the
+// register budget: F = FeCall keeps the loop I-cache resident; MINB blocks/SM bounds registers (2 -> 255, 3 -> 168, 4 -> 128).
+template <class F, int MINB>
+__global__ void __launch_bounds__(ED_THREADS, MINB)
 k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs,
             const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
     __shared__ ge_precomp sB[8];                 // (j+1)B, j = 0..7: 768 bytes
@@ -63,7 +68,7 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
     load_words8(sig, sigs + 64ull * i);
     load_words8(sig + 8, sigs + 64ull * i + 32);
     load_words8(k, (const uint8_t*)(ks + 8ull * i));
-    ok[i] = (uint8_t)ed25519_verify_core(pk, sig, k, sB);
+    ok[i] = (uint8_t)ed25519_verify_core<F>(pk, sig, k, sB);
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
@@ -76,13 +81,13 @@ k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys,
     if (mode == 0) {
         uint32_t seed[8];
         load_words8(seed, keys + 32ull * i);
-        ed25519_expand(s, prefix, pk, seed, comb);
+        ed25519_expand<FeCall>(s, prefix, pk, seed, comb);
     } else {
         const uint8_t* e = keys + 96ull * (key_index ? key_index[i] : i);
         load_words8(s, e); load_words8(prefix, e + 32); load_words8(pk, e + 64);
     }
     uint64_t o0 = off[i], o1 = off[i + 1];
-    ed25519_sign_expanded(sig, s, prefix, pk, msgs + o0, o1 - o0, comb);
+    ed25519_sign_expanded<FeCall>(sig, s, prefix, pk, msgs + o0, o1 - o0, comb);
     store_words8(sigs + 64ull * i, sig);
     store_words8(sigs + 64ull * i + 32, sig + 8);
 }
@@ -95,7 +100,7 @@ k_ed_expand(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ see
     if (i >= n) return;
     uint32_t seed[8], s[8], prefix[8], pk[8];
     load_words8(seed, seeds + 32ull * i);
-    ed25519_expand(s, prefix, pk, seed, comb);
+    ed25519_expand<FeCall>(s, prefix, pk, seed, comb);
     if (expanded96) {
         uint8_t* e = expanded96 + 96ull * i;
         store_words8(e, s); store_words8(e + 32, prefix); store_words8(e + 64, pk);
@@ -161,6 +166,71 @@ __global__ void k_microbench_fe(int which, uint32_t iters, uint32_t* sink) {
         for (uint32_t it = 0; it < iters; it++) { fe_add(a, a, b); fe_sub(b, b, a); }
     } else if (which == 5) {
         for (uint32_t it = 0; it < iters; it++) { fe_mul_c(a, a, b); fe_mul_c(b, b, a); }
+    } else if (which == 6) {
+        for (uint32_t it = 0; it < iters; it++) { fe_mul(a, a, a); fe_mul(b, b, b); }
+    } else if (which == 10) {
+        // raw pipe probes (2 * 8 instructions per iteration): 8 independent IMAD.WIDE.U32 accumulators
+        uint64_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = ((uint64_t)a.v[i] << 32) | b.v[i];
+        uint32_t m0 = a.v[0] | 1, m1 = b.v[1] | 1;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = (uint64_t)m0 * (uint32_t)(m1 + i) + acc[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a.v[i] ^= (uint32_t)acc[i]; b.v[i] ^= (uint32_t)(acc[i] >> 32); }
+    } else if (which == 11) {
+        // 16 IMAD (32-bit) per iteration
+        uint32_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = a.v[i];
+        uint32_t m0 = a.v[0] | 1;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = acc[i] * m0 + b.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) a.v[i] ^= acc[i];
+    } else if (which == 12) {
+        // 16 LOP3/IADD3-class ALU instructions per iteration
+        uint32_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = a.v[i];
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = (acc[i] + b.v[i]) ^ (acc[(i + 1) & 7] & b.v[(i + 3) & 7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) a.v[i] ^= acc[i];
+    } else if (which == 13) {
+        // 8 IMAD.WIDE + 8 carry-chain adds per iteration (both pipes)
+        uint64_t acc[4];
+        uint32_t s[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = ((uint64_t)a.v[i] << 32) | b.v[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = b.v[i];
+        uint32_t m0 = a.v[0] | 1, m1 = b.v[1] | 1;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] = (uint64_t)m0 * (uint32_t)(m1 + i) + acc[i];
+#pragma unroll
+                for (int i = 0; i < 4; i++) s[2 * r + i] = (s[2 * r + i] + a.v[i]) ^ (s[(i + 5) & 7] & 0x55555555u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a.v[i] ^= (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) b.v[i] ^= s[i];
     } else {
         for (uint32_t it = 0; it < iters; it++) { fe_mul(a, a, a); fe_mul(b, b, b); }
     }
@@ -184,7 +254,17 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
                             uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
-    AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, pks, sigs, scratch_k, n, ok));
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("AFC_VERIFY_VARIANT"); variant = e ? atoi(e) : 1; }
+    const ge_precomp* cb = (const ge_precomp*)comb;
+    const uint32_t nb = blocks_for(n, ED_THREADS);
+    switch (variant) {
+    case 0: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 2><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    case 2: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 4><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    case 3: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 3><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    case 4: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 2><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 3><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    }
     return cudaGetLastError();
 }
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,

@@ -37,6 +37,26 @@ METRIC = "credential Ed25519 verifies/sec (512B payload)"
 UNIT = "verifies/s"
 
 
+def host_threads():
+    """CPU threads this process may actually use: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for qf, pf in (("/sys/fs/cgroup/cpu.max", None), ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us")):
+        try:
+            if pf is None:
+                q, per = open(qf).read().split()
+            else:
+                q, per = open(qf).read().strip(), open(pf).read().strip()
+            if q not in ("max", "-1"):
+                n = max(1, min(n, int(float(q) / float(per) + 0.999)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -137,6 +157,9 @@ def cpu_reference_rate(threads, budget_s=12.0):
 
     pk, sg, ms, off = sample(4096 * max(1, threads // 8))
     t0 = time.perf_counter()
+    CO.ed25519_verify_batch(pk[:2048], sg[:2048], ms, off[:2049], 1)
+    cpu_reference_rate.single_thread = 2048 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
     CO.ed25519_verify_batch(pk, sg, ms, off, threads)
     rate0 = (len(off) - 1) / (time.perf_counter() - t0)
     m = int(min(N_ITEMS, max(8192, rate0 * budget_s)))
@@ -151,7 +174,7 @@ def cpu_reference_rate(threads, budget_s=12.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     # each step = one bounded sample; scale the per-step budget so warmup+steps end within a few minutes
     budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     rates, sample = [], 0
@@ -167,7 +190,8 @@ def run_reference(args, rank, world):
                                         "items_per_step": sample, "msg_len": MSG_LEN, "keys": N_KEYS, "corrupted": "1%"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d credentials per step; oracle/afc_oracle.c (C restatement of Go crypto/ed25519: 51-bit limbs, NAF vartime "
-                                   "double-scalar mult), %d pthreads; Go toolchain absent so the reference itself cannot run" % (sample, threads)},
+                                   "double-scalar mult), %d pthreads (one thread alone: %.0f/s); Go toolchain absent so the reference itself "
+                                   "cannot run" % (sample, threads, cpu_reference_rate.single_thread)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -291,11 +315,11 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         rate, sample = cpu_reference_rate(threads, 12.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d credentials of the same workload; oracle/afc_oracle.c (C restatement of Go crypto/ed25519), %d pthreads"
-                                          % (sample, threads)}
+                                "sample": "%d credentials of the same workload; oracle/afc_oracle.c (C restatement of Go crypto/ed25519), %d pthreads "
+                                          "(one thread alone: %.0f/s)" % (sample, threads, cpu_reference_rate.single_thread)}
     if args.extras:
         line["extras"] = extras(ctx, dev, world, rank)
     if rank == 0:
@@ -366,7 +390,9 @@ def extras(ctx, dev, world, rank):
         out["merkle_global_root"] = afb.fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx).hex()
     mb = {}
     for name, which, iters in (("fe_mul", 0, 4000), ("fe_sq", 1, 4000), ("fe_addsub", 2, 20000), ("fe_mul_portable", 5, 2000),
-                               ("fe_sq_via_mul", 6, 4000), ("sha256_compress", 3, 2000), ("sha512_compress", 4, 1000)):
+                               ("fe_sq_via_mul", 6, 4000), ("sha256_compress", 3, 2000), ("sha512_compress", 4, 1000),
+                               ("pipe_imad_wide_x16", 10, 20000), ("pipe_imad32_x16", 11, 20000), ("pipe_alu_x16", 12, 20000),
+                               ("pipe_mix_wide8_alu8", 13, 20000)):
         ops, ms = ctx.microbench(which, iters)
         mb[name] = {"ops_per_s": ops, "ms": ms}
     out["microbench"] = mb
