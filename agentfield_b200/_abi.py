@@ -14,7 +14,7 @@ AFC_OK, AFC_EINVAL, AFC_ECUDA, AFC_ENOMEM, AFC_ENCCL, AFC_ESTATE = 0, -1, -2, -3
 MERKLE_STATE_BYTES = 8 + 64 * 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafcrypto.so")
+LIB_PATH = os.environ.get("AFC_LIB", os.path.join(_HERE, "libafcrypto.so"))   # AFC_LIB: experiment builds only
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)

@@ -347,7 +347,100 @@ AFC_HD void fe_mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
 #endif
 }
 
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+// r[0..7] = a[0..3] * b[0..3] (256-bit product) with the same even/odd carry-chain scheme: 16 IMAD.WIDE + 10 adds.
+__device__ __forceinline__ void mul4x4_ptx(uint32_t* r, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    uint32_t E0, E1, E2, E3, E4, E5, E6, E7, O0, O1, O2, O3, O4, O5, O6;
+    // row 0
+    asm("mul.lo.u32 %0, %8, %12;\n\tmul.hi.u32 %1, %8, %12;\n\tmul.lo.u32 %2, %10, %12;\n\tmul.hi.u32 %3, %10, %12;\n\t"
+        "mul.lo.u32 %4, %9, %12;\n\tmul.hi.u32 %5, %9, %12;\n\tmul.lo.u32 %6, %11, %12;\n\tmul.hi.u32 %7, %11, %12;"
+        : "=r"(E0), "=r"(E1), "=r"(E2), "=r"(E3), "=r"(O0), "=r"(O1), "=r"(O2), "=r"(O3)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0));
+    // row 1: E (2,3) += a1 b1, (4,5) fresh a3 b1;  O (0,1) += a0 b1, (2,3) += a2 b1, carry -> O4
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\tmadc.hi.cc.u32 %1, %4, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %6, 0;\n\tmadc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(E2), "+r"(E3), "=r"(E4), "=r"(E5) : "r"(a1), "r"(a3), "r"(b1));
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(O0), "+r"(O1), "+r"(O2), "+r"(O3), "=r"(O4) : "r"(a0), "r"(a2), "r"(b1));
+    // row 2: E (2,3) += a0 b2, (4,5) += a2 b2, carry -> E6;  O (2,3) += a1 b2, (4,5): O4 += lo, O5 fresh (a3 b2)
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(E2), "+r"(E3), "+r"(E4), "+r"(E5), "=r"(E6) : "r"(a0), "r"(a2), "r"(b2));
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\tmadc.hi.cc.u32 %1, %4, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(O2), "+r"(O3), "+r"(O4), "=r"(O5) : "r"(a1), "r"(a3), "r"(b2));
+    // row 3: E (4,5) += a1 b3, (6,7): E6 += lo, E7 fresh (a3 b3);  O (2,3) += a0 b3, (4,5) += a2 b3, carry -> O6
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\tmadc.hi.cc.u32 %1, %4, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %6, %2;\n\tmadc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(E4), "+r"(E5), "+r"(E6), "=r"(E7) : "r"(a1), "r"(a3), "r"(b3));
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(O2), "+r"(O3), "+r"(O4), "+r"(O5), "=r"(O6) : "r"(a0), "r"(a2), "r"(b3));
+    // r = E + (O << 32)
+    r[0] = E0;
+    asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\taddc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\taddc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(E1), "r"(E2), "r"(E3), "r"(E4), "r"(E5), "r"(E6), "r"(E7), "r"(O0), "r"(O1), "r"(O2), "r"(O3), "r"(O4), "r"(O5), "r"(O6));
+}
+
+// One-level Karatsuba: 3 x (4x4) = 48 IMAD.WIDE instead of 64, paid for with ~60 adds on the otherwise idle ALU pipe
+// (ncu on sm_100a: the 64-bit multiplier pipe "fmaheavy" is the binding unit, IMAD.WIDE issues once per 4 cycles/SMSP).
+__device__ __forceinline__ void fe_mul_wide_kara(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+    uint32_t L[8], H[8], M[9];
+    mul4x4_ptx(L, a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]);
+    mul4x4_ptx(H, a[4], a[5], a[6], a[7], b[4], b[5], b[6], b[7]);
+    uint32_t sa0, sa1, sa2, sa3, ca, sb0, sb1, sb2, sb3, cb;
+    asm("add.cc.u32 %0, %5, %9;\n\taddc.cc.u32 %1, %6, %10;\n\taddc.cc.u32 %2, %7, %11;\n\taddc.cc.u32 %3, %8, %12;\n\taddc.u32 %4, 0, 0;"
+        : "=r"(sa0), "=r"(sa1), "=r"(sa2), "=r"(sa3), "=r"(ca) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+    asm("add.cc.u32 %0, %5, %9;\n\taddc.cc.u32 %1, %6, %10;\n\taddc.cc.u32 %2, %7, %11;\n\taddc.cc.u32 %3, %8, %12;\n\taddc.u32 %4, 0, 0;"
+        : "=r"(sb0), "=r"(sb1), "=r"(sb2), "=r"(sb3), "=r"(cb) : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    mul4x4_ptx(M, sa0, sa1, sa2, sa3, sb0, sb1, sb2, sb3);
+    // (sa + ca W)(sb + cb W) = M + (ca sb + cb sa) W + ca cb W^2      (W = 2^128)
+    uint32_t ma = 0u - ca, mb = 0u - cb;
+    uint32_t x0 = (sb0 & ma), x1 = (sb1 & ma), x2 = (sb2 & ma), x3 = (sb3 & ma);
+    uint32_t y0 = (sa0 & mb), y1 = (sa1 & mb), y2 = (sa2 & mb), y3 = (sa3 & mb);
+    uint32_t m8 = ca & cb;
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(m8) : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(m8) : "r"(y0), "r"(y1), "r"(y2), "r"(y3));
+    M[8] = m8;
+    // cross = M - L - H  (non-negative, < 2^258)
+    asm("sub.cc.u32 %0, %0, %9;\n\tsubc.cc.u32 %1, %1, %10;\n\tsubc.cc.u32 %2, %2, %11;\n\tsubc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\tsubc.cc.u32 %5, %5, %14;\n\tsubc.cc.u32 %6, %6, %15;\n\tsubc.cc.u32 %7, %7, %16;\n\tsubc.u32 %8, %8, 0;"
+        : "+r"(M[0]), "+r"(M[1]), "+r"(M[2]), "+r"(M[3]), "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8])
+        : "r"(L[0]), "r"(L[1]), "r"(L[2]), "r"(L[3]), "r"(L[4]), "r"(L[5]), "r"(L[6]), "r"(L[7]));
+    asm("sub.cc.u32 %0, %0, %9;\n\tsubc.cc.u32 %1, %1, %10;\n\tsubc.cc.u32 %2, %2, %11;\n\tsubc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\tsubc.cc.u32 %5, %5, %14;\n\tsubc.cc.u32 %6, %6, %15;\n\tsubc.cc.u32 %7, %7, %16;\n\tsubc.u32 %8, %8, 0;"
+        : "+r"(M[0]), "+r"(M[1]), "+r"(M[2]), "+r"(M[3]), "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8])
+        : "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]), "r"(H[4]), "r"(H[5]), "r"(H[6]), "r"(H[7]));
+    // t = L + cross W + H W^2
+    t[0] = L[0]; t[1] = L[1]; t[2] = L[2]; t[3] = L[3];
+    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, 0;\n\taddc.cc.u32 %10, %22, 0;\n\taddc.u32 %11, %23, 0;"
+        : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]),
+          "=r"(t[14]), "=r"(t[15])
+        : "r"(L[4]), "r"(L[5]), "r"(L[6]), "r"(L[7]), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]), "r"(H[4]), "r"(H[5]), "r"(H[6]), "r"(H[7]),
+          "r"(M[0]), "r"(M[1]), "r"(M[2]), "r"(M[3]), "r"(M[4]), "r"(M[5]), "r"(M[6]), "r"(M[7]), "r"(M[8]));
+}
+#endif
+
+#ifndef AFC_FE_KARATSUBA
+#define AFC_FE_KARATSUBA 0      // measured on B200: 375 vs 332 cycles per warp-multiply — the extra adds do not overlap
+#endif
+
 AFC_HD void fe_mul(fe& h, const fe& f, const fe& g) {
+    uint32_t t[16];
+#if AFC_DEVICE_CODE && AFC_FE_PTX && AFC_FE_KARATSUBA
+    fe_mul_wide_kara(t, f.v, g.v);
+#else
+    fe_mul_wide(t, f.v, g.v);
+#endif
+    fe_fold16(h, t);
+}
+// the 64-product schoolbook form, kept for the microbenchmark comparison
+AFC_HD void fe_mul_schoolbook(fe& h, const fe& f, const fe& g) {
     uint32_t t[16];
     fe_mul_wide(t, f.v, g.v);
     fe_fold16(h, t);

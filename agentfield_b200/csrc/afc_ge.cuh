@@ -7,9 +7,9 @@
 //
 // GPU shape (differs from Go's variable-time NAF on purpose): every lane of a warp must run the same
 // instruction stream, so the double-scalar multiplication R' = [S]B + [k](-A) uses FIXED signed radix-16
-// windows for both scalars over one shared doubling chain (Straus): 252 doublings, 64 additions from a
-// per-credential table of 8 cached multiples of -A (thread-local), and 64 mixed additions from an
-// 8-entry affine table of B (768 B, staged in shared memory).  Results are bit-identical to Go's because
+// windows over one shared doubling chain (Straus): 252 doublings, 64 additions from a per-credential table of
+// 8 cached multiples of -A (4-bit digits, thread-local), and 32 mixed additions from a 128-entry affine table of
+// B (8-bit digits, 12 KB staged in shared memory).  Results are bit-identical to Go's because
 // both compute the same group element and compare canonical encodings.
 #pragma once
 #include "afc_fe.cuh"
@@ -123,46 +123,49 @@ AFC_HD int ge_frombytes(ge_p3& h, const uint32_t* enc) {
     return ok_pos | ok_neg;
 }
 
-// Tables of multiples of the base point, built on the device at afc_init (see k_ed25519.cu):
-//   b8[j]          = (j+1) B                 j = 0..7          (verify: Straus with shared doublings)
-//   comb[i][j]     = (j+1) 16^i B            i = 0..63, j=0..7 (sign / pubkey: no doublings)
-struct BaseTables {
-    const ge_precomp* b8;
-    const ge_precomp* comb;
-};
+// Table of multiples of the base point, built on the device at afc_init (k_ed_build_tables), radix 256:
+//   comb[i][j] = (j+1) * 256^i * B     i = 0..31, j = 0..127   affine precomputed form, 4096 x 96 B = 384 KB (L2-resident)
+// Row 0 (the 128 small multiples of B, 12 KB) is what verification stages in shared memory.
+static constexpr int COMB_ROWS = 32, COMB_COLS = 128;
 
-
-// Row i of the fixed-base table: row[j] = (j+1) * 16^i * B in affine precomputed form.  One thread per
-// row at afc_init (k_build_tables); row 0 doubles as the 8-entry table b8 used by verification.
+// One table entry per thread at init: (j+1) * 256^i * B.
 template <class F = FeInline>
-AFC_HD void ge_build_comb_row(ge_precomp* row, int i) {
+AFC_HD void ge_build_comb_entry(ge_precomp& out, int i, int j) {
     ge_p3 P, M;
     fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); F::mul(P.T, P.X, P.Y);
     ge_p1p1 t;
-    for (int k = 0; k < 4 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
+#pragma unroll 1
+    for (int k = 0; k < 8 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
+    // M = (j+1) P by left-to-right double-and-add over the 8 bits of (j+1)
     ge_cached c;
     ge_p3_to_cached<F>(c, P);
+    int m = j + 1, started = 0;
     M = P;
-    for (int j = 0; j < 8; j++) {
-        ge_p3_to_precomp<F>(row[j], M);
-        ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
+#pragma unroll 1
+    for (int bit = 7; bit >= 0; bit--) {
+        if (started) { ge_dbl<F>(t, M.X, M.Y, M.Z); ge_p1p1_to_p3<F>(M, t); }
+        if ((m >> bit) & 1) {
+            if (started) { ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t); }
+            else { M = P; started = 1; }
+        }
     }
+    ge_p3_to_precomp<F>(out, M);
 }
 
-// h = a * B for a reduced scalar a (< 2^253): 64 mixed additions, no doublings.
+// h = a * B for a reduced scalar a (< 2^253): 32 mixed additions (signed radix-256 digits), no doublings.
 template <class F = FeInline>
 AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* comb) {
     uint32_t t[8];
-    sc_recode16(t, a);
+    sc_recode256(t, a);
     ge_p3_0(h);
 #pragma unroll 1
-    for (int i = 0; i < 64; i++) {
-        int d = sc_digit16(t, i);
+    for (int i = 0; i < 32; i++) {
+        int d = sc_digit256(t, i);
         if (d != 0) {
             int neg = d < 0;
             int m = neg ? -d : d;
             ge_p1p1 r;
-            ge_maddsub<F>(r, h, comb[i * 8 + (m - 1)], neg);
+            ge_maddsub<F>(r, h, comb[i * COMB_COLS + (m - 1)], neg);
             ge_p1p1_to_p3<F>(h, r);
         }
     }
@@ -172,7 +175,7 @@ AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* co
 // pk, sig: little-endian words of the given byte strings; k = SHA-512(R || A || M) mod L.
 // Returns 1 iff Go's ed25519.Verify would return true.
 template <class F = FeInline>
-AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const uint32_t* k, const ge_precomp* b8) {
+AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const uint32_t* k, const ge_precomp* b128) {
     int ok = 1;
     if (sig[15] & 0xE0000000u) ok = 0;                 // sig[63] & 224 != 0
     if (!sc_is_canonical(sig + 8)) ok = 0;             // S >= L
@@ -192,7 +195,7 @@ AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const ui
     }
     uint32_t kt[8], st[8];
     sc_recode16(kt, k);
-    sc_recode16(st, sig + 8);
+    sc_recode256(st, sig + 8);
     // Straus over one shared doubling chain.  The running point lives in P1xP1 form (t) between steps: it is completed
     // to P3 (4 mul) only right before an addition needs T, and to P2 (3 mul) before doublings.
     ge_p2 q;
@@ -215,13 +218,13 @@ AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const ui
             ge_p1p1_to_p3<F>(r, t);
             ge_addsub<F>(t, r, tab[m - 1], neg);
         }
-        int ds = sc_digit16(st, i);
+        int ds = (i & 1) ? 0 : sc_digit256(st, i >> 1);     // S advances 8 bits every second 4-bit step
         if (ds != 0) {
             int neg = ds < 0;
             int m = neg ? -ds : ds;
             ge_p3 r;
             ge_p1p1_to_p3<F>(r, t);
-            ge_maddsub<F>(t, r, b8[m - 1], neg);
+            ge_maddsub<F>(t, r, b128[m - 1], neg);
         }
     }
     ge_p1p1_to_p2<F>(q, t);

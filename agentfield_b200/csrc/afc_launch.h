@@ -49,7 +49,7 @@ cudaError_t merkle_root(const uint8_t* frontier, uint64_t size, uint8_t* out32, 
 cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg);
 
 // ---- k_ed25519.cu
-struct EdTables { void* comb; };     // 64*8 ge_precomp (row 0 = b8)
+// comb: 32 x 128 ge_precomp (row 0 = the 128 small multiples of B)
 size_t ed_tables_bytes();
 cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg);
 // scratch_k: n * 32 bytes

@@ -96,4 +96,12 @@ AFC_HD void sc_recode16(uint32_t* t, const uint32_t* s) {
 }
 AFC_HD int sc_digit16(const uint32_t* t, int i) { return (int)((t[i >> 3] >> ((i & 7) * 4)) & 15u) - 8; }
 
+// Signed radix-256 recoding of s < 2^254: t = s + 0x80..80; digit_i = byte_i(t) - 128 in [-128, 127].
+AFC_HD void sc_recode256(uint32_t* t, const uint32_t* s) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)s[i] + 0x80808080u; t[i] = (uint32_t)c; c >>= 32; }
+}
+AFC_HD int sc_digit256(const uint32_t* t, int i) { return (int)((t[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
+
 }  // namespace afc

@@ -30,26 +30,38 @@ AFC_HD uint32_t maj32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (x 
 #define AFC_OUTLINE static __device__ __noinline__
 #endif
 
-// One compression: st += F(st, w[0..15]) — w is consumed (used as the rolling schedule window).
-// Rounds are unrolled 16 at a time (4 trips): schedule indices stay compile-time, K comes from the constant bank.
-AFC_OUTLINE void sha256_compress(uint32_t* st, uint32_t* w) {
-    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#pragma unroll 1
-    for (int r = 0; r < 64; r += 16) {
+// One compression: st += F(st, w[0..15]).  Fully unrolled (round constants become constant-bank immediates, the
+// schedule window stays in registers); ONE out-of-line copy per kernel, state and block passed in registers.
+struct sha256_io { uint32_t st[8]; uint32_t w[16]; };
+struct sha256_st { uint32_t st[8]; };
+AFC_OUTLINE sha256_st sha256_compress_regs(sha256_io x) {
+    uint32_t a = x.st[0], b = x.st[1], c = x.st[2], d = x.st[3], e = x.st[4], f = x.st[5], g = x.st[6], h = x.st[7];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (r > 0) {
-                uint32_t w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
-                uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-                uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-                w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
-            }
-            uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[r + j] + w[j];
-            uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
-            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = x.w[(i - 15) & 15], w2 = x.w[(i - 2) & 15];
+            uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            x.w[i & 15] = x.w[i & 15] + s0 + x.w[(i - 7) & 15] + s1;
         }
+        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[i] + x.w[i & 15];
+        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
-    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    sha256_st r;
+    r.st[0] = x.st[0] + a; r.st[1] = x.st[1] + b; r.st[2] = x.st[2] + c; r.st[3] = x.st[3] + d;
+    r.st[4] = x.st[4] + e; r.st[5] = x.st[5] + f; r.st[6] = x.st[6] + g; r.st[7] = x.st[7] + h;
+    return r;
+}
+AFC_HD void sha256_compress(uint32_t* st, uint32_t* w) {
+    sha256_io x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.st[i] = st[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x.w[i] = w[i];
+    sha256_st r = sha256_compress_regs(x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = r.st[i];
 }
 
 AFC_HD void sha256_init(uint32_t st[8]) {

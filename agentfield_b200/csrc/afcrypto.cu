@@ -810,7 +810,7 @@ int afc_microbench(afc_ctx* ctx, int which, uint32_t iters, double* ops_per_s, d
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     CK(e);
-    double per_thread = (which == 3 || which == 4) ? 1.0 : (which >= 10 ? 16.0 : 2.0);   // fe probes: 2 ops / iteration; pipe probes: 16 instr
+    double per_thread = (which == 3 || which == 4) ? 1.0 : (which >= 20 ? 1.0 : (which >= 10 ? 16.0 : 2.0));   // fe probes: 2 ops / iteration; pipe probes: 16 instr
     *ops_per_s = (double)blocks * threads * iters * per_thread / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
     return AFC_OK;

@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -201,7 +201,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -248,7 +248,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count()
-    ctx.profile_begin(max(256, 96 * (args.steps + 2)))
+    ctx.profile_begin(max(256, 96 * (args.steps + 2)))      # per-kernel CUDA events on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -390,11 +390,16 @@ def extras(ctx, dev, world, rank):
         out["merkle_global_root"] = afb.fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx).hex()
     mb = {}
     for name, which, iters in (("fe_mul", 0, 4000), ("fe_sq", 1, 4000), ("fe_addsub", 2, 20000), ("fe_mul_portable", 5, 2000),
-                               ("fe_sq_via_mul", 6, 4000), ("sha256_compress", 3, 2000), ("sha512_compress", 4, 1000),
+                               ("fe_sq_via_mul", 6, 4000), ("fe_mul_schoolbook", 7, 4000), ("sha256_compress", 3, 2000), ("sha512_compress", 4, 1000),
                                ("pipe_imad_wide_x16", 10, 20000), ("pipe_imad32_x16", 11, 20000), ("pipe_alu_x16", 12, 20000),
-                               ("pipe_mix_wide8_alu8", 13, 20000)):
+                               ("pipe_mix_wide8_alu8", 13, 20000),
+                               ("probe_w8_a0", 20, 20000), ("probe_w8_a8", 21, 20000), ("probe_w8_a16", 22, 20000), ("probe_w8_a24", 23, 20000),
+                               ("probe_w8_a32", 24, 20000), ("probe_w8_a48", 29, 20000), ("probe_w8_carrypairs16", 25, 20000),
+                               ("probe_w8_xor16", 26, 20000), ("probe_wX8_a0", 27, 20000), ("probe_wX8_a16", 28, 20000)):
         ops, ms = ctx.microbench(which, iters)
         mb[name] = {"ops_per_s": ops, "ms": ms}
+        if which >= 20:     # cycles per iteration per warp on one SMSP (32 warps/SM in the probe grid: 8 per SMSP)
+            mb[name]["cycles_per_iter_per_smsp_warp"] = ms * 1e-3 * 1.965e9 / iters / 8
     out["microbench"] = mb
     return out
 

@@ -16,8 +16,9 @@ using namespace afc;
 static std::vector<ge_precomp> g_comb;
 static void ensure_tables() {
     if (!g_comb.empty()) return;
-    g_comb.resize(64 * 8);
-    for (int i = 0; i < 64; i++) ge_build_comb_row(&g_comb[i * 8], i);
+    g_comb.resize(COMB_ROWS * COMB_COLS);
+    for (int i = 0; i < COMB_ROWS; i++)
+        for (int j = 0; j < COMB_COLS; j++) ge_build_comb_entry(g_comb[i * COMB_COLS + j], i, j);
 }
 static void words_from_bytes(uint32_t* w, const uint8_t* b, int n) { for (int i = 0; i < n; i++) w[i] = load_le32(b + 4 * i); }
 static void bytes_from_words(uint8_t* b, const uint32_t* w, int n) { for (int i = 0; i < n; i++) store_le32(b + 4 * i, w[i]); }
