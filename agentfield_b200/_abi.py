@@ -46,6 +46,11 @@ SYMBOLS = {
     "afc_ed25519_expand_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
     "afc_ed25519_sign_expanded_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]),
     "afc_ed25519_sign_expanded_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
+    "afc_keyset_new": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
+    "afc_keyset_free": (None, [vp]),
+    "afc_keyset_info": (C.c_int, [vp, u32p, u64p]),
+    "afc_ed25519_verify_keyed_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp]),
+    "afc_ed25519_verify_keyed_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_merkle_new": (C.c_int, [vp, C.POINTER(vp)]),
     "afc_merkle_free": (None, [vp]),
     "afc_merkle_append": (C.c_int, [vp, vp, vp, C.c_uint32, vp, u64p]),

@@ -236,6 +236,66 @@ AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const ui
     return ok & (diff == 0);
 }
 
+
+// ---------------------------------------------------------------------------------- keyed verification (identity cache, N1)
+// When the verifier already knows the issuer key (the reference resolves every issuer DID from its own registry,
+// vc_service.go:259 -> did_service.go:368), a per-key radix-256 table of -A makes the variable-base half as cheap as
+// the fixed-base half: R' = sum_i ks_i * (256^i B) + sum_i kk_i * (256^i (-A)) = 64 mixed additions, no doublings.
+//
+// One row of a key's table per thread: row[j] = (j+1) * 256^i * (-A), affine precomputed form.  Returns 0 if the key
+// does not decode (Go: verification with that key is always false).
+template <class F = FeInline>
+AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
+    ge_p3 P, M;
+    int ok = ge_frombytes<F>(P, pk);
+    fe_neg(P.X, P.X); fe_neg(P.T, P.T);
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int k = 0; k < 8 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
+    ge_cached c;
+    ge_p3_to_cached<F>(c, P);
+    M = P;
+#pragma unroll 1
+    for (int j = 0; j < COMB_COLS; j++) {
+        ge_p3_to_precomp<F>(row[j], M);
+        ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
+    }
+    return ok;
+}
+
+// pk_ok: the key decoded; atab: that key's 32 x 128 table of -A; comb: the base-point table.
+template <class F = FeInline>
+AFC_HD int ed25519_verify_keyed_core(int pk_ok, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* comb) {
+    int ok = pk_ok;
+    if (sig[15] & 0xE0000000u) ok = 0;
+    if (!sc_is_canonical(sig + 8)) ok = 0;
+    uint32_t kt[8], st[8];
+    sc_recode256(kt, k);
+    sc_recode256(st, sig + 8);
+    ge_p3 h; ge_p3_0(h);
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        int dk = sc_digit256(kt, i), ds = sc_digit256(st, i);
+        if (dk != 0) {
+            int neg = dk < 0, m = neg ? -dk : dk;
+            ge_maddsub<F>(t, h, atab[i * COMB_COLS + (m - 1)], neg);
+            ge_p1p1_to_p3<F>(h, t);
+        }
+        if (ds != 0) {
+            int neg = ds < 0, m = neg ? -ds : ds;
+            ge_maddsub<F>(t, h, comb[i * COMB_COLS + (m - 1)], neg);
+            ge_p1p1_to_p3<F>(h, t);
+        }
+    }
+    uint32_t enc[8];
+    ge_encode<F>(enc, h.X, h.Y, h.Z);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) diff |= enc[i] ^ sig[i];
+    return ok & (diff == 0);
+}
+
 // k = SHA-512(R || A || M) mod L
 AFC_HD void ed25519_hram(uint32_t* k, const uint32_t* pk, const uint32_t* sig, const uint8_t* msg, uint64_t len) {
     uint32_t pre[16], dig[16];

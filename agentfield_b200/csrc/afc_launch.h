@@ -55,6 +55,11 @@ cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg);
 // scratch_k: n * 32 bytes
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                             uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
+size_t ed_key_table_bytes(uint32_t n_keys);
+cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
+                                  const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                                  uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                           uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, const uint32_t* key_index, const uint8_t* msgs,

@@ -89,6 +89,15 @@ struct afc_ctx {
     uint8_t* d_comm_buf = nullptr;
 };
 
+struct afc_keyset {
+    afc_ctx* ctx = nullptr;
+    uint32_t n_keys = 0;
+    uint8_t* d_pks = nullptr;      // n_keys x 32
+    uint8_t* d_valid = nullptr;    // n_keys
+    void* d_tabs = nullptr;        // n_keys x 32 x 128 ge_precomp
+    size_t tab_bytes = 0;
+};
+
 struct afc_merkle {
     afc_ctx* ctx = nullptr;
     uint64_t size = 0;
@@ -169,7 +178,7 @@ cudaError_t h2d(Slot& sl, void* dst, const void* src, size_t bytes, bool pinned,
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-enum Op { OP_SHA256, OP_HMAC, OP_VERIFY, OP_SIGN, OP_SIGN_EXP, OP_LEAF };
+enum Op { OP_SHA256, OP_HMAC, OP_VERIFY, OP_SIGN, OP_SIGN_EXP, OP_LEAF, OP_VERIFY_KEYED };
 
 struct BatchArgs {
     Op op;
@@ -177,7 +186,8 @@ struct BatchArgs {
     const uint8_t* a = nullptr; size_t a_item = 0;     // per-item fixed-size input (pks / seeds)
     const uint8_t* b = nullptr; size_t b_item = 0;     // second per-item input (sigs)
     const uint8_t* keys = nullptr; const uint32_t* koff = nullptr;   // HMAC keys
-    const uint8_t* d_expanded = nullptr; const uint32_t* key_index = nullptr;  // sign-expanded
+    const uint8_t* d_expanded = nullptr; const uint32_t* key_index = nullptr;  // sign-expanded / keyed verify
+    const afc_keyset* keyset = nullptr;
     uint8_t* out; size_t out_item;
 };
 
@@ -218,21 +228,21 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         CK(sl.out.reserve((size_t)cnt * A.out_item + 16));
         if (A.a) CK(sl.a.reserve((size_t)cnt * A.a_item + 16));
         if (A.b) CK(sl.b.reserve((size_t)cnt * A.b_item + 16));
-        if (A.op == OP_VERIFY) CK(sl.k.reserve((size_t)cnt * 32));
+        if (A.op == OP_VERIFY || A.op == OP_VERIFY_KEYED) CK(sl.k.reserve((size_t)cnt * 32));
         uint32_t kbase = 0; size_t kbytes = 0;
         if (A.op == OP_HMAC) {
             kbase = A.koff[i0]; kbytes = A.koff[i1] - kbase;
             CK(sl.a.reserve(kbytes + 16));
             CK(sl.koff.reserve((size_t)(cnt + 1) * 4));
         }
-        if (A.op == OP_SIGN_EXP && A.key_index) CK(sl.koff.reserve((size_t)cnt * 4));
+        if ((A.op == OP_SIGN_EXP || A.op == OP_VERIFY_KEYED) && A.key_index) CK(sl.koff.reserve((size_t)cnt * 4));
         size_t bounce = 0;
         if (!pin_msgs) bounce += (mbytes + 255) & ~(size_t)255;
         if (!pin_off) bounce += ((size_t)(cnt + 1) * 8 + 255) & ~(size_t)255;
         if (A.a && !pin_a) bounce += ((size_t)cnt * A.a_item + 255) & ~(size_t)255;
         if (A.b && !pin_b) bounce += ((size_t)cnt * A.b_item + 255) & ~(size_t)255;
         if (A.op == OP_HMAC) { if (!pin_keys) bounce += (kbytes + 255) & ~(size_t)255; if (!pin_koff) bounce += ((size_t)(cnt + 1) * 4 + 255) & ~(size_t)255; }
-        if (A.op == OP_SIGN_EXP && A.key_index && !pin_ki) bounce += ((size_t)cnt * 4 + 255) & ~(size_t)255;
+        if ((A.op == OP_SIGN_EXP || A.op == OP_VERIFY_KEYED) && A.key_index && !pin_ki) bounce += ((size_t)cnt * 4 + 255) & ~(size_t)255;
         CK(sl.h_in.reserve(bounce + 256));
         if (!pin_out) CK(sl.h_out.reserve((size_t)cnt * A.out_item));
         size_t used = 0;
@@ -258,6 +268,12 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         case OP_VERIFY:
             e = launch::ed_verify_batch(ctx->comb, sl.a.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
             break;
+        case OP_VERIFY_KEYED: {
+            CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used));
+            e = launch::ed_verify_keyed_batch(ctx->comb, A.keyset->d_tabs, A.keyset->d_valid, A.keyset->d_pks, A.keyset->n_keys,
+                                              (const uint32_t*)sl.koff.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
+            break;
+        }
         case OP_SIGN: e = launch::ed_sign_batch(ctx->comb, sl.a.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
         case OP_SIGN_EXP: {
             const uint32_t* d_ki = nullptr;
@@ -481,6 +497,69 @@ int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint
     if (!aligned16(d_out32)) return AFC_EINVAL;
     CK(launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, d_out32, st, lc));
     DEV_EPILOGUE();
+}
+
+
+// ---------------------------------------------------------------------------------- keyed verification
+int afc_keyset_new(afc_ctx* ctx, const uint8_t* pks, uint32_t n_keys, afc_keyset** out) {
+    if (!ctx || !out || !pks || n_keys == 0) return AFC_EINVAL;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    afc_keyset* ks = new (std::nothrow) afc_keyset();
+    if (!ks) return AFC_ENOMEM;
+    ks->ctx = ctx; ks->n_keys = n_keys; ks->tab_bytes = launch::ed_key_table_bytes(n_keys);
+    cudaError_t e = cudaMalloc((void**)&ks->d_pks, (size_t)n_keys * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ks->d_valid, n_keys);
+    if (e == cudaSuccess) e = cudaMalloc(&ks->d_tabs, ks->tab_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(ks->d_pks, pks, (size_t)n_keys * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        CallLog lc(ctx);
+        e = launch::ed_build_key_tables(ks->d_pks, n_keys, ks->d_tabs, ks->d_valid, 0, lc);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+        set_err(ctx, e, "afc_keyset_new");
+        afc_keyset_free(ks);
+        return e == cudaErrorMemoryAllocation ? AFC_ENOMEM : AFC_ECUDA;
+    }
+    *out = ks;
+    return AFC_OK;
+}
+void afc_keyset_free(afc_keyset* ks) {
+    if (!ks) return;
+    cudaSetDevice(ks->ctx->device);
+    if (ks->d_pks) cudaFree(ks->d_pks);
+    if (ks->d_valid) cudaFree(ks->d_valid);
+    if (ks->d_tabs) cudaFree(ks->d_tabs);
+    delete ks;
+}
+int afc_keyset_info(afc_keyset* ks, uint32_t* n_keys, uint64_t* table_bytes) {
+    if (!ks) return AFC_EINVAL;
+    if (n_keys) *n_keys = ks->n_keys;
+    if (table_bytes) *table_bytes = ks->tab_bytes;
+    return AFC_OK;
+}
+int afc_ed25519_verify_keyed_batch(afc_ctx* ctx, afc_keyset* ks, const uint32_t* key_index, const uint8_t* sigs,
+                                   const uint8_t* msgs, const uint64_t* msg_off, uint32_t n, uint8_t* ok) {
+    if (!ctx || !ks || ks->ctx != ctx || !msg_off || (n && (!key_index || !sigs || !ok))) return AFC_EINVAL;
+    BatchArgs A{}; A.op = OP_VERIFY_KEYED; A.msgs = msgs; A.off = msg_off; A.n = n; A.b = sigs; A.b_item = 64; A.key_index = key_index;
+    A.keyset = ks; A.out = ok; A.out_item = 1;
+    return run_host_batch(ctx, A);
+}
+int afc_ed25519_verify_keyed_batch_dev(afc_ctx* ctx, afc_keyset* ks, const uint32_t* d_key_index, const uint8_t* d_sigs,
+                                       const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_ok, void* stream) {
+    if (!ctx || !ks || ks->ctx != ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!aligned16(d_sigs)) return AFC_EINVAL;
+    CallLog lc(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* d_k = nullptr;
+    if (n) CK(cudaMallocAsync((void**)&d_k, (size_t)n * 32, st));
+    cudaError_t e = launch::ed_verify_keyed_batch(ctx->comb, ks->d_tabs, ks->d_valid, ks->d_pks, ks->n_keys, d_key_index, d_sigs, d_msgs,
+                                                  d_msg_off, n, d_ok, d_k, st, lc);
+    if (n) cudaFreeAsync(d_k, st);
+    CK(e);
+    return AFC_OK;
 }
 
 // ---------------------------------------------------------------------------------- Merkle log

@@ -71,6 +71,52 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
     ok[i] = (uint8_t)ed25519_verify_core<F>(pk, sig, k, sB);
 }
 
+
+// ---- keyed verification (identity cache): per-key radix-256 tables of -A, built once per key set
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_key_rows(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_precomp* __restrict__ tabs, uint8_t* __restrict__ valid) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keys * COMB_ROWS) return;
+    uint32_t key = t / COMB_ROWS, row = t % COMB_ROWS;
+    uint32_t pk[8];
+    load_words8(pk, pks + 32ull * key);
+    int ok = ge_build_key_row<FeCall>(tabs + ((size_t)key * COMB_ROWS + row) * COMB_COLS, pk, (int)row);
+    if (row == 0) valid[key] = (uint8_t)ok;
+}
+
+__global__ void __launch_bounds__(ED_THREADS)
+k_ed_hram_keyed(const uint8_t* __restrict__ key_pks, const uint32_t* __restrict__ key_index, uint32_t n_keys,
+                const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n,
+                uint32_t* __restrict__ k_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = key_index[i];
+    if (key >= n_keys) key = 0;                   // result is forced to 0 in k_ed_verify_keyed
+    uint32_t pk[8], sig[16], k[8];
+    load_words8(pk, key_pks + 32ull * key);
+    load_words8(sig, sigs + 64ull * i);
+    uint64_t o0 = off[i], o1 = off[i + 1];
+    ed25519_hram(k, pk, sig, msgs + o0, o1 - o0);
+    store_words8((uint8_t*)(k_out + 8ull * i), k);
+}
+
+__global__ void __launch_bounds__(ED_THREADS, 3)
+k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
+                  const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
+                  const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = key_index[i];
+    int pk_ok = key < n_keys;
+    if (!pk_ok) key = 0;
+    pk_ok &= (int)valid[key];
+    uint32_t sig[16], k[8];
+    load_words8(sig, sigs + 64ull * i);
+    load_words8(sig + 8, sigs + 64ull * i + 32);
+    load_words8(k, (const uint8_t*)(ks + 8ull * i));
+    ok[i] = (uint8_t)ed25519_verify_keyed_core<FeInline>(pk_ok, sig, k, tabs + (size_t)key * COMB_ROWS * COMB_COLS, comb);
+}
+
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, int mode,
@@ -311,6 +357,21 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
     case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 3><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
     default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 2><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
     }
+    return cudaGetLastError();
+}
+
+size_t ed_key_table_bytes(uint32_t n_keys) { return sizeof(ge_precomp) * (size_t)n_keys * COMB_ROWS * COMB_COLS; }
+cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg) {
+    if (n_keys == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_key_rows", s, k_ed_key_rows<<<blocks_for((uint64_t)n_keys * COMB_ROWS, ED_THREADS), ED_THREADS, 0, s>>>(pks, n_keys, (ge_precomp*)tabs, valid));
+    return cudaGetLastError();
+}
+cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
+                                  const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                                  uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
+    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok));
     return cudaGetLastError();
 }
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,

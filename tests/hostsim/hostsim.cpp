@@ -70,6 +70,23 @@ int hs_verify(const uint8_t pk[32], const uint8_t* msg, uint64_t len, const uint
     ed25519_hram(k, p, s, msg, len);
     return ed25519_verify_core(p, s, k, &g_comb[0]);
 }
+// keyed path: build the per-key table on the CPU (slow, test only) and verify through it
+int hs_verify_keyed(const uint8_t pk[32], const uint8_t* msg, uint64_t len, const uint8_t sig[64]) {
+    ensure_tables();
+    static std::vector<ge_precomp> atab;
+    static uint8_t cached_pk[32];
+    static int cached_ok = -1;
+    uint32_t p[8], s[16], k[8];
+    words_from_bytes(p, pk, 8); words_from_bytes(s, sig, 16);
+    if (cached_ok < 0 || memcmp(cached_pk, pk, 32) != 0) {
+        atab.resize(COMB_ROWS * COMB_COLS);
+        int ok = 1;
+        for (int i = 0; i < COMB_ROWS; i++) ok &= ge_build_key_row(&atab[i * COMB_COLS], p, i);
+        cached_ok = ok; memcpy(cached_pk, pk, 32);
+    }
+    ed25519_hram(k, p, s, msg, len);
+    return ed25519_verify_keyed_core(cached_ok, s, k, &atab[0], &g_comb[0]);
+}
 void hs_pubkey(const uint8_t seed[32], uint8_t pk[32]) {
     ensure_tables();
     uint32_t sd[8], s[8], pre[8], p[8]; words_from_bytes(sd, seed, 8);

@@ -217,6 +217,94 @@ def test_merkle_fold_of_aligned_shard_roots(ctx):
             assert fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx) == full, (n, world)
 
 
+def test_keyed_verify_equals_generic_verify_and_go_rules(ctx):
+    """N1 identity cache: per-key tables must give bit-identical accept/reject decisions, edge keys included."""
+    from agentfield_b200 import KeySet
+    es = golden("ed25519_edge.json") + [dict(e, valid=True) for e in golden("rfc8032.json")]
+    pks = sorted({e["pk"] for e in es})
+    ks = KeySet([bytes.fromhex(p) for p in pks], ctx)
+    assert ks.info()["n_keys"] == len(pks)
+    ok = ks.verify_batch([bytes.fromhex(e["pk"]) for e in es], [bytes.fromhex(e["msg"]) for e in es], [bytes.fromhex(e["sig"]) for e in es])
+    for e, o in zip(es, ok):
+        assert o == e["valid"], e["name"]
+    ks.close()
+    # random keys, ragged messages, corruption in every field; out-of-range key index -> 0
+    rng = np.random.default_rng(0xAF12)
+    nk, n = 64, 4000
+    seeds = rng.integers(0, 256, (nk, 32), dtype=np.uint8)
+    kpks = ctx.pubkeys(seeds)
+    ki = rng.integers(0, nk, n).astype(np.uint32)
+    lens = rng.integers(0, 900, n)
+    off = np.zeros(n + 1, dtype=np.uint64); off[1:] = np.cumsum(lens)
+    buf = rng.integers(0, 256, int(off[-1]) + 1, dtype=np.uint8)
+    sigs = ctx.sign_packed(seeds[ki].copy(), buf, off)
+    idx = np.arange(n)
+    sigs[idx % 7 == 0, 9] ^= 2
+    sigs[idx % 7 == 3, 50] ^= 0x40
+    ks = KeySet([bytes(p) for p in kpks], ctx)
+    got = ks.verify_packed(ki, sigs, buf, off)
+    exp = ctx.verify_packed(kpks[ki].copy(), sigs, buf, off)
+    assert (got == exp).all() and (exp == CO.ed25519_verify_batch(kpks[ki].copy(), sigs, buf, off, 8)).all()
+    ki2 = ki.copy(); ki2[::11] = nk + 5
+    got2 = ks.verify_packed(ki2, sigs, buf, off)
+    assert not got2[::11].any() and (np.delete(got2, np.arange(0, n, 11)) == np.delete(exp, np.arange(0, n, 11))).all()
+    ks.close()
+
+
+def test_expanded_key_cache_derivation_matches_reference_flow(ctx):
+    from agentfield_b200 import ExpandedKeys
+    g = golden("reference_flow.json")
+    cache = ExpandedKeys(ctx)
+    dids = cache.derive(bytes.fromhex(g["master_seed"]), [d["path"] for d in g["derivations"]])
+    assert dids == [d["did"] for d in g["derivations"]]
+    vc = g["vc"]
+    assert cache.sign_batch([dids[1]], [vc["canonical"].encode()])[0].hex() == vc["sig"]
+
+
+def test_config1_issue_and_verify_1000_vcs_reference_flow(ctx):
+    """BASELINE.json configs[0]: issue + verify 1 000 synthetic 512 B agent-action VCs.  The GPU path (services.VCService over
+    the key cache) must produce byte-identical vc_document / signature to the CPU restatement of the reference flow
+    (oracle/ref_vc.py, OpenSSL signatures) and accept / reject exactly like it."""
+    import json
+    from test_host_logic import _vc_requests
+    from agentfield_b200 import ExpandedKeys, go_json
+    from agentfield_b200.services import VCService, generate_webhook_signature_batch
+    from oracle import ref_vc, go_hash as H
+    rng = np.random.default_rng(0xAF01)
+    master = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    paths = ["m/44'/0'"] + ["m/44'/%d'/%d'" % (1237 + a, 0) for a in range(16)] + ["m/44'/%d'/0'/0'/0'" % (1237 + a) for a in range(16)] + \
+            ["m/44'/%d'/0'/1'/0'" % (1237 + a) for a in range(16)]
+    cache = ExpandedKeys(ctx)
+    dids = cache.derive(master, paths)
+    seeds = {d: H.derive_seed(master, p) for d, p in zip(dids, paths)}
+    assert all(d == H.did_key(CO.pubkey(seeds[d])) for d in dids[:5])
+    reqs = _vc_requests(1000, dids[1:], rng)
+    svc = VCService(cache, ctx)
+    issued = svc.generate_execution_vc_batch(reqs)
+    canon_lens = set()
+    for r, got in zip(reqs, issued):
+        exp = ref_vc.generate_execution_vc(r, seeds[r["caller_did"]])
+        assert got["vc_document"] == exp["vc_document"] and got["signature"] == exp["signature"]
+        canon_lens.add(len(exp["canonical"]))
+    assert canon_lens == {512}
+    ok = svc.verify_vc_batch(issued)
+    assert all(ok) and all(ref_vc.verify_vc(v["vc_document"], cache.public_key(v["doc"]["issuer"])) for v in issued[:50])
+    # tamper: change a field of the parsed document / swap signatures
+    bad = [dict(v, doc=json.loads(json.dumps(v["doc"]))) for v in issued[:100]]
+    for i, v in enumerate(bad):
+        if i % 2:
+            v["doc"]["credentialSubject"]["execution"]["status"] = "tampered"
+        else:
+            v["proof"] = dict(v["proof"], proofValue=issued[(i + 1) % 100]["proof"]["proofValue"])
+    assert not any(svc.verify_vc_batch(bad))
+    # webhook header shape
+    bodies = [go_json.webhook_payload({"event": "execution.completed", "execution_id": r["execution_id"], "workflow_id": r["workflow_id"],
+                                       "status": r["status"], "target": "node.fn", "type": "reasoner", "duration_ms": r["duration_ms"],
+                                       "result": None, "error_message": r["error_message"], "timestamp": r["timestamp"]}) for r in reqs[:200]]
+    secrets = ["secret-%d" % (i % 5) for i in range(200)]
+    assert generate_webhook_signature_batch(secrets, bodies, ctx) == [H.webhook_signature(s, b) for s, b in zip(secrets, bodies)]
+
+
 # ----------------------------------------------------------------------------- device-pointer (resident) variants
 def test_device_resident_variants_equal_host_variants(ctx):
     import torch

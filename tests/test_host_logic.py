@@ -105,3 +105,47 @@ def test_merkle_exchange_step_world2_gloo(n):
     for p in ps:
         p.join(60)
     assert len(res) == 2 and all(f == full for _, f, full in res) and res[0][1] == res[1][1]
+
+
+def _vc_requests(n, dids, rng, pad_to=512):
+    """Synthetic GenerateExecutionVC inputs; executionId padded so the canonical form is exactly `pad_to` bytes (cfg1)."""
+    from oracle import ref_vc, go_hash as H
+    reqs = []
+    for i in range(n):
+        r = {"vc_id": "vc-%019d" % (1789971100759287000 + i), "caller_did": dids[i % len(dids)], "target_did": dids[(i + 1) % len(dids)],
+             "agent_node_did": dids[0], "caller_type": "agent", "function_name": "fn_%d" % (i % 7), "issuance_date": "2026-09-21T06:00:00Z",
+             "execution_id": "exec_%06d" % i, "workflow_id": "wf_%04d" % (i // 10), "session_id": "sess_%04d" % (i // 100),
+             "input": rng.integers(0, 256, int(rng.integers(0, 64)), dtype=np.uint8).tobytes() if i % 5 else None,
+             "output": rng.integers(0, 256, int(rng.integers(0, 64)), dtype=np.uint8).tobytes(), "status": "succeeded" if i % 9 else "failed",
+             "error_message": None if i % 9 else "boom <&> \u2028 \"x\"", "duration_ms": int(rng.integers(0, 5000)),
+             "timestamp": "2026-09-21T06:00:%02dZ" % (i % 60), "proof_created": "2026-09-21T06:00:01Z"}
+        if pad_to:
+            ih = H.hash_data(H.marshal_data_or_null(r["input"])); oh = H.hash_data(H.marshal_data_or_null(r["output"]))
+            cur = len(ref_vc.go_marshal(ref_vc.vc_document(r, ih, oh)))
+            if cur < pad_to:
+                r["execution_id"] += "x" * (pad_to - cur)
+        reqs.append(r)
+    return reqs
+
+
+def test_go_json_restatement_two_constructions_agree():
+    """agentfield_b200/go_json.py (string builder) vs oracle/ref_vc.py (json module + escapes): same canonical bytes."""
+    from agentfield_b200 import go_json
+    from oracle import ref_vc
+    rng = np.random.default_rng(0xAF01)
+    dids = ["did:key:z%s" % ("A" * 46), "did:key:z%s" % ("B" * 46), "did:key:z%s" % ("C" * 46)]
+    for r in _vc_requests(200, dids, rng, pad_to=0):
+        doc = ref_vc.vc_document(r, "ih-%s" % r["vc_id"], "oh")
+        a = ref_vc.go_marshal(doc)
+        d2 = dict(doc); d2["credentialSubject"] = dict(doc["credentialSubject"])
+        d2["credentialSubject"]["execution"] = dict(doc["credentialSubject"]["execution"])
+        d2["credentialSubject"]["execution"].setdefault("errorMessage", "")
+        assert go_json.vc_document(d2) == a
+        assert go_json.vc_document(d2, {"type": "T", "created": "c", "verificationMethod": "v", "proofPurpose": "p", "proofValue": "s"}) == \
+            ref_vc.go_marshal(dict(doc, proof={"type": "T", "created": "c", "verificationMethod": "v", "proofPurpose": "p", "proofValue": "s"}))
+    assert go_json.string("a<b>&c\u2028\x01\b\f\"\\") == '"a\\u003cb\\u003e\\u0026c\\u2028\\u0001\\b\\f\\"\\\\"'
+    assert [go_json.number(x) for x in (0.1, 1e-7, 1e21, 42.0, 123456789.125, 3)] == ["0.1", "1e-7", "1e+21", "42", "123456789.125", "3"]
+    assert go_json.value({"b": [1, "x", None, True], "a": {"z": 1.5}}) == '{"a":{"z":1.5},"b":[1,"x",null,true]}'
+    wp = go_json.webhook_payload({"event": "execution.completed", "execution_id": "e", "workflow_id": "w", "status": "succeeded", "target": "n.fn",
+                                  "type": "reasoner", "duration_ms": 12, "result": {"k": "<v>"}, "error_message": None, "timestamp": "t"})
+    assert wp == b'{"event":"execution.completed","execution_id":"e","workflow_id":"w","status":"succeeded","target":"n.fn","type":"reasoner","duration_ms":12,"result":{"k":"\\u003cv\\u003e"},"timestamp":"t"}'
