@@ -11,7 +11,8 @@ from ._abi import AfcError, LIB_PATH
 from .crypto import Context, Hasher, MAC, Signer, Verifier, default_context, pack, pack32
 from .audit import Auditor, fold_roots
 from .identity import ExpandedKeys, KeySet, did_key
+from .dispatcher import Ingest
 
 __all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "fold_roots",
-           "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key"]
+           "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key", "Ingest"]
 __version__ = "0.1.0"

@@ -66,11 +66,26 @@ SYMBOLS = {
     "afc_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "afc_comm_allgather_roots": (C.c_int, [vp, vp, vp]),
     "afc_comm_destroy": (C.c_int, [vp]),
+    "afc_b64url_encode_fixed_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "afc_hex_encode_fixed_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "afc_ingest_new": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "afc_ingest_free": (None, [vp]),
+    "afc_ingest_submit": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, u64p]),
+    "afc_ingest_wait": (C.c_int, [vp, C.c_uint64, vp, vp]),
+    "afc_ingest_flush": (C.c_int, [vp]),
+    "afc_ingest_stats_get": (C.c_int, [vp, vp]),
+    "afc_ingest_soak": (C.c_int, [vp, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.POINTER(C.c_double), u64p]),
     "afc_selftest": (C.c_int, [vp, C.c_uint32]),
     "afc_profile_begin": (C.c_int, [vp, C.c_int]),
     "afc_profile_end": (C.c_int, [vp, vp, C.c_int]),
     "afc_microbench": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
+
+
+class IngestStats(C.Structure):
+    _fields_ = [("submitted", C.c_uint64), ("completed", C.c_uint64), ("batches", C.c_uint64), ("avg_batch", C.c_double),
+                ("p50_us", C.c_uint32), ("p99_us", C.c_uint32), ("max_us", C.c_uint32), ("log_size", C.c_uint64),
+                ("log_root", C.c_uint8 * 32), ("last_error", C.c_int)]
 
 
 class ProfileEntry(C.Structure):

@@ -177,6 +177,12 @@ class Context:
         _abi.check(self._lib.afc_ed25519_sign_expanded_batch_dev(self.handle, _abi.ptr(d_expanded96), _abi.ptr(d_key_index), _abi.ptr(d_msgs),
                                                                  _abi.ptr(d_off), n, _abi.ptr(d_sigs), self._stream(stream)), self.handle)
 
+    def b64url_encode_dev(self, d_in, item_bytes, n, d_out, stream=None):
+        _abi.check(self._lib.afc_b64url_encode_fixed_dev(self.handle, _abi.ptr(d_in), item_bytes, n, _abi.ptr(d_out), self._stream(stream)), self.handle)
+
+    def hex_encode_dev(self, d_in, item_bytes, n, d_out, stream=None):
+        _abi.check(self._lib.afc_hex_encode_fixed_dev(self.handle, _abi.ptr(d_in), item_bytes, n, _abi.ptr(d_out), self._stream(stream)), self.handle)
+
     def merkle_leaf_hashes_dev(self, d_leaves, d_off, n, d_out, stream=None):
         _abi.check(self._lib.afc_merkle_leaf_hashes_dev(self.handle, _abi.ptr(d_leaves), _abi.ptr(d_off), n, _abi.ptr(d_out),
                                                         self._stream(stream)), self.handle)

@@ -5,6 +5,7 @@
 // There is deliberately NO CPU implementation of any primitive in this library: if CUDA is missing or
 // fails, calls return AFC_ECUDA and the reference-side adapter decides what to do.
 #include "../../include/afcrypto.h"
+#include "afc_internal.h"
 #include "afc_launch.h"
 
 #include <atomic>
@@ -296,6 +297,10 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
 
 }  // namespace
 
+int afc_internal_device(afc_ctx* ctx) { return ctx->device; }
+const void* afc_internal_comb(afc_ctx* ctx) { return ctx->comb; }
+void afc_internal_add_launches(afc_ctx* ctx, unsigned long long n) { ctx->launches += n; }
+
 extern "C" {
 
 const char* afc_version(void) { return "afcrypto-b200 0.1.0 (sm_100a)"; }
@@ -499,6 +504,19 @@ int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint
     DEV_EPILOGUE();
 }
 
+
+int afc_b64url_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream) {
+    DEV_PROLOGUE();
+    if (n && item_bytes && (!d_in || !d_out)) return AFC_EINVAL;
+    CK(launch::b64url_encode(d_in, item_bytes, n, d_out, st, lc));
+    DEV_EPILOGUE();
+}
+int afc_hex_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream) {
+    DEV_PROLOGUE();
+    if (n && item_bytes && (!d_in || !d_out)) return AFC_EINVAL;
+    CK(launch::hex_encode(d_in, (uint64_t)item_bytes * n, d_out, st, lc));
+    DEV_EPILOGUE();
+}
 
 // ---------------------------------------------------------------------------------- keyed verification
 int afc_keyset_new(afc_ctx* ctx, const uint8_t* pks, uint32_t n_keys, afc_keyset** out) {

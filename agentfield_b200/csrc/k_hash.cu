@@ -108,6 +108,40 @@ __global__ void k_merkle_root(const uint8_t* __restrict__ frontier, uint64_t siz
     store_digest256(out, acc);
 }
 
+
+// ---- text codecs either side of the kernels: base64url without padding for signatures / digests
+// (base64.RawURLEncoding in vc_service.go:465,514) and lowercase hex for the webhook header (hex.EncodeToString,
+// webhook_dispatcher.go:473).  Fixed-size records; one thread per 3-byte group / per byte pair.
+__global__ void __launch_bounds__(256)
+k_b64url_encode(const uint8_t* __restrict__ in, uint32_t item, uint32_t n, uint8_t* __restrict__ out) {
+    const uint32_t groups = (item + 2) / 3, out_item = (item * 4 + 2) / 3;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * groups) return;
+    uint32_t rec = (uint32_t)(t / groups), g = (uint32_t)(t % groups);
+    const uint8_t* p = in + (uint64_t)rec * item + 3 * g;
+    uint32_t rem = item - 3 * g;
+    uint32_t v = (uint32_t)p[0] << 16;
+    if (rem > 1) v |= (uint32_t)p[1] << 8;
+    if (rem > 2) v |= p[2];
+    uint8_t* o = out + (uint64_t)rec * out_item + 4 * g;
+    uint32_t nch = rem >= 3 ? 4 : rem + 1;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        if (k < nch) {
+            uint32_t x = (v >> (18 - 6 * k)) & 63u;
+            o[k] = (uint8_t)(x < 26 ? 'A' + x : x < 52 ? 'a' + (x - 26) : x < 62 ? '0' + (x - 52) : (x == 62 ? '-' : '_'));
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+k_hex_encode(const uint8_t* __restrict__ in, uint64_t total, uint8_t* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    uint32_t b = in[t], hi = b >> 4, lo = b & 15;
+    out[2 * t] = (uint8_t)(hi < 10 ? '0' + hi : 'a' + (hi - 10));
+    out[2 * t + 1] = (uint8_t)(lo < 10 ? '0' + lo : 'a' + (lo - 10));
+}
+
 // register-only throughput probes: which = 3 SHA-256 compress, 4 SHA-512 compress
 __global__ void k_microbench_hash(int which, uint32_t iters, uint32_t* sink) {
     uint32_t seed = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +195,17 @@ cudaError_t merkle_level(const uint8_t* in, uint8_t* out, uint64_t npairs, int l
 }
 cudaError_t merkle_root(const uint8_t* frontier, uint64_t size, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
     AFC_LAUNCH(lg, "k_merkle_root", s, k_merkle_root<<<1, 32, 0, s>>>(frontier, size, out32));
+    return cudaGetLastError();
+}
+cudaError_t b64url_encode(const uint8_t* in, uint32_t item, uint32_t n, uint8_t* out, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0 || item == 0) return cudaSuccess;
+    uint64_t threads = (uint64_t)n * ((item + 2) / 3);
+    AFC_LAUNCH(lg, "k_b64url_encode", s, k_b64url_encode<<<blocks_for(threads, 256), 256, 0, s>>>(in, item, n, out));
+    return cudaGetLastError();
+}
+cudaError_t hex_encode(const uint8_t* in, uint64_t total, uint8_t* out, cudaStream_t s, LaunchLog* lg) {
+    if (total == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_hex_encode", s, k_hex_encode<<<blocks_for(total, 256), 256, 0, s>>>(in, total, out));
     return cudaGetLastError();
 }
 cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg) {

@@ -158,6 +158,41 @@ int afc_comm_init(afc_ctx* ctx, int nranks, int rank, const uint8_t id128[128]);
 int afc_comm_allgather_roots(afc_ctx* ctx, const uint8_t local_root32[32], uint8_t* all_roots /* nranks x 32 */);
 int afc_comm_destroy(afc_ctx* ctx);
 
+/* ---- N3: text codecs either side of the kernels (device pointers) ------------------------------------------------------
+ * base64.RawURLEncoding of signatures / digests (internal/services/vc_service.go:465,514) and hex.EncodeToString of the
+ * webhook tag (internal/services/webhook_dispatcher.go:473) for n fixed-size records of item_bytes each.
+ * out: n x ceil(item_bytes*4/3) characters (no padding), resp. n x 2*item_bytes lowercase hex characters. */
+int afc_b64url_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream);
+int afc_hex_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream);
+
+/* ---- N2: batching ingest dispatcher (BASELINE.json configs[4]: sustained mixed ingest) ------------------------------
+ * One "agent action" = Ed25519 signature over the credential bytes (expanded key `key_index` of the identity cache) +
+ * HMAC-SHA256 webhook tag + one audit-log leaf (the signature) appended to an RFC 6962 log owned by the dispatcher.
+ * Replaces the reference's one-per-request issuing (internal/handlers/did_handlers.go:192 ->
+ * internal/services/vc_service.go:138) and its 4-goroutine webhook worker pool (internal/services/webhook_dispatcher.go:
+ * 97-128, 261-320) with GPU batches: flush at `batch_max` actions or after `linger_us`.  Thread-safe; submit blocks only
+ * when both staging buffers are full (back-pressure). */
+typedef struct afc_ingest afc_ingest;
+typedef struct afc_ingest_stats {
+    uint64_t submitted, completed, batches;
+    double avg_batch;
+    uint32_t p50_us, p99_us, max_us;       /* submit -> results-on-host latency */
+    uint64_t log_size;
+    uint8_t log_root[32];
+    int last_error;
+} afc_ingest_stats;
+int afc_ingest_new(afc_ctx* ctx, const uint8_t* expanded96, uint32_t n_keys, uint32_t batch_max, uint32_t linger_us,
+                   uint32_t max_msg, uint32_t max_key, uint32_t max_body, afc_ingest** out);
+void afc_ingest_free(afc_ingest* g);
+int afc_ingest_submit(afc_ingest* g, uint32_t key_index, const uint8_t* msg, uint32_t msg_len, const uint8_t* hkey, uint32_t hkey_len,
+                      const uint8_t* body, uint32_t body_len, uint64_t* ticket);
+int afc_ingest_wait(afc_ingest* g, uint64_t ticket, uint8_t sig64[64], uint8_t tag32[32]);
+int afc_ingest_flush(afc_ingest* g);
+int afc_ingest_stats_get(afc_ingest* g, afc_ingest_stats* out);
+/* native open-loop load generator: Poisson arrivals at rate_per_s for `seconds` from `producers` threads (32-byte HMAC keys) */
+int afc_ingest_soak(afc_ingest* g, double rate_per_s, double seconds, uint32_t producers, uint32_t msg_len, uint32_t body_len,
+                    uint64_t seed, afc_ingest_stats* out, double* achieved_rate, uint64_t* late_submits);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * afc_selftest: runs the PTX field arithmetic against the portable reference ON THE DEVICE for `iters`
  * random operands (returns number of mismatches, or negative error).

@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""Runs each hot-path kernel once at its bench size (after one warm-up each) so that one `ncu --set full` pass captures them all."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import agentfield_b200 as afb
+import bench
+
+dev = torch.device("cuda", 0)
+ctx = afb.Context(0)
+d_pks, d_sigs, d_msgs, d_off, expect = bench.make_workload(ctx, dev, 0)
+n = bench.N_ITEMS
+d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
+ks = afb.KeySet([bytes(p) for p in d_pks[:bench.N_KEYS].cpu().numpy()], ctx)
+d_ki = (torch.arange(n, device=dev) % bench.N_KEYS).to(torch.int32)
+g = torch.Generator(device=dev); g.manual_seed(1)
+m = 4_000_000
+bodies = torch.randint(0, 256, (m, 256), dtype=torch.uint8, device=dev, generator=g)
+keys = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=g)
+boff = torch.arange(m + 1, device=dev, dtype=torch.int64) * 256
+koff = (torch.arange(m + 1, device=dev, dtype=torch.int64) * 32).to(torch.int32)
+tags = torch.empty((m, 32), dtype=torch.uint8, device=dev)
+ns = 1 << 19
+kseeds = torch.randint(0, 256, (bench.N_KEYS, 32), dtype=torch.uint8, device=dev, generator=g)
+d_exp = torch.empty((bench.N_KEYS, 96), dtype=torch.uint8, device=dev)
+seeds_full = kseeds[(torch.arange(ns, device=dev) % bench.N_KEYS)].contiguous()
+ski = (torch.arange(ns, device=dev) % bench.N_KEYS).to(torch.int32)
+sigs2 = torch.empty((ns, 64), dtype=torch.uint8, device=dev)
+soff = torch.arange(ns + 1, device=dev, dtype=torch.int64) * 64
+root = torch.empty(32, dtype=torch.uint8, device=dev)
+for rep in range(2):
+    ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)
+    ks.verify_dev(d_ki, d_sigs, d_msgs, d_off, n, d_ok)
+    ctx.hmac_sha256_dev(keys.view(-1), koff, bodies.view(-1), boff, m, tags)
+    ctx.sha256_dev(bodies.view(-1), boff, m, tags)
+    ctx.expand_dev(kseeds, bench.N_KEYS, d_exp)
+    ctx.sign_expanded_dev(d_exp, ski, d_msgs, d_off, ns, sigs2)
+    ctx.sign_dev(seeds_full, d_msgs, d_off, ns, sigs2)
+    a = afb.Auditor(ctx)
+    a.append_dev(sigs2.view(-1), soff, ns)
+    a.root_dev(root)
+    torch.cuda.synchronize()
+    a.close()
+print("done")
