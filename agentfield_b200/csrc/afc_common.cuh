@@ -109,6 +109,20 @@ struct PadStream {
     }
 };
 
+// 128-bit read-only load of 16 message bytes (16-byte aligned): one LDG.E.128 instead of four LDG.E.32
+struct word4 { uint32_t x, y, z, w; };
+AFC_HD word4 ld_u128(const uint8_t* p) {
+#if AFC_DEVICE_CODE
+    uint4 v = __ldg((const uint4*)p);
+    word4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+#else
+    word4 r;
+    memcpy(&r, p, 16);
+    return r;
+#endif
+}
+
 AFC_HD void store_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 AFC_HD uint32_t load_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 AFC_HD void store_le32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }

@@ -71,9 +71,25 @@ AFC_HD void sha256_init(uint32_t st[8]) {
 
 // Absorb `len` message bytes after `prior` bytes have already been compressed into st (prior % 64 == 0),
 // then pad and finish.  st holds the digest words (big-endian order) on return.
+// Whole 64-byte blocks of a 16-byte-aligned message take the lean path: four 128-bit loads + 16 byte swaps, no per-word
+// bounds / padding logic (these kernels are ALU-bound: every instruction saved in block loading is throughput).
 AFC_HD void sha256_finish_stream(uint32_t st[8], const uint8_t* msg, uint64_t len, uint64_t prior) {
-    PadStream ps; ps.init(msg, len);
     uint64_t total = prior + len;
+    if ((((uintptr_t)msg) & 15) == 0) {
+        uint64_t nfull = len >> 6;
+        for (uint64_t blk = 0; blk < nfull; blk++) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                word4 v = ld_u128(msg + 16 * q);
+                w[4 * q] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+            }
+            sha256_compress(st, w);
+            msg += 64;
+        }
+        len &= 63;
+    }
+    PadStream ps; ps.init(msg, len);
     uint64_t nblk = (len + 9 + 63) / 64;
     for (uint64_t blk = 0; blk < nblk; blk++) {
         uint32_t w[16];
@@ -219,20 +235,51 @@ AFC_OUTLINE void sha512_compress(uint64_t* st, uint64_t* w) {
 }
 
 // SHA-512( prefix (PW 32-bit words, given as LITTLE-endian-loaded words of the byte string) || msg ).
-// PW must be even and <= 24.  Digest returned as 64 bytes little-endian-loaded into 16 u32 (i.e. the
+// PW must be a multiple of 4 and <= 24.  Digest returned as 64 bytes little-endian-loaded into 16 u32 (i.e. the
 // digest byte string viewed as LE words — the form the scalar reduction wants).
 template <int PW>
 AFC_HD void sha512_prefixed(uint32_t digest_le[16], const uint32_t* prefix_le, const uint8_t* msg, uint64_t len) {
-    static_assert(PW % 2 == 0 && PW <= 24, "prefix must be whole 64-bit words and leave room in block 0");
+    static_assert(PW % 4 == 0 && PW <= 24, "prefix must be whole 16-byte groups and leave room in block 0");
     uint64_t st[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) st[i] = AFC_H512[i];
+    const uint64_t total = (uint64_t)PW * 4 + len;
+    constexpr int M0 = 128 - 4 * PW;                   // message bytes that share block 0 with the prefix
+    bool first_done = false;
+    if ((((uintptr_t)msg) & 15) == 0 && len >= (uint64_t)M0) {
+        // lean path: block 0 = prefix || msg[0:M0], then whole 128-byte blocks, all with 128-bit loads
+        uint64_t w[16];
+#pragma unroll
+        for (int i = 0; i < PW / 2; i++) w[i] = ((uint64_t)bswap32(prefix_le[2 * i]) << 32) | bswap32(prefix_le[2 * i + 1]);
+#pragma unroll
+        for (int q = 0; q < M0 / 16; q++) {
+            word4 v = ld_u128(msg + 16 * q);
+            w[PW / 2 + 2 * q] = ((uint64_t)bswap32(v.x) << 32) | bswap32(v.y);
+            w[PW / 2 + 2 * q + 1] = ((uint64_t)bswap32(v.z) << 32) | bswap32(v.w);
+        }
+        sha512_compress(st, w);
+        msg += M0; len -= M0;
+        first_done = true;
+        uint64_t nfull = len >> 7;
+        for (uint64_t blk = 0; blk < nfull; blk++) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                word4 v = ld_u128(msg + 16 * q);
+                w[2 * q] = ((uint64_t)bswap32(v.x) << 32) | bswap32(v.y);
+                w[2 * q + 1] = ((uint64_t)bswap32(v.z) << 32) | bswap32(v.w);
+            }
+            sha512_compress(st, w);
+            msg += 128;
+        }
+        len &= 127;
+    }
+    // general path: (the rest of) the message through the byte-granular padded stream
     PadStream ps; ps.init(msg, len);
-    uint64_t total = (uint64_t)PW * 4 + len;
-    uint64_t nblk = (total + 17 + 127) / 128;
+    const uint64_t pending = first_done ? len : total;            // bytes still to absorb, prefix included if not yet done
+    const uint64_t nblk = (pending + 17 + 127) / 128;
     for (uint64_t blk = 0; blk < nblk; blk++) {
         uint64_t w[16];
-        if (blk == 0) {
+        if (blk == 0 && !first_done) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 uint32_t hi, lo;
@@ -241,7 +288,7 @@ AFC_HD void sha512_prefixed(uint32_t digest_le[16], const uint32_t* prefix_le, c
                 w[i] = ((uint64_t)hi << 32) | lo;
             }
         } else {
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 16; i++) {
                 uint32_t hi = ps.next_be(), lo = ps.next_be();
                 w[i] = ((uint64_t)hi << 32) | lo;
