@@ -9,10 +9,10 @@ runs in libafcrypto.so on the GPU; there is no CPU fallback in this package (see
 from . import _abi
 from ._abi import AfcError, LIB_PATH
 from .crypto import Context, Hasher, MAC, Signer, Verifier, default_context, pack, pack32
-from .audit import Auditor, fold_roots
+from .audit import Auditor, MerkleTree, fold_roots, verify_inclusion_batch
 from .identity import ExpandedKeys, KeySet, did_key
 from .dispatcher import Ingest
 
-__all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "fold_roots",
+__all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "MerkleTree", "fold_roots", "verify_inclusion_batch",
            "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key", "Ingest"]
 __version__ = "0.1.0"

@@ -97,3 +97,63 @@ def fold_roots(subtree_roots, ctx=None):
         return root
     finally:
         a.close()
+
+
+class MerkleTree:
+    """afc_merkle_tree: every level kept on the device over a fixed set of leaf hashes, for bulk audit paths (N4)."""
+
+    def __init__(self, leaf_hashes, ctx=None):
+        self.ctx = ctx or default_context()
+        self._lib = _abi.load()
+        h = C.c_void_p()
+        if hasattr(leaf_hashes, "data_ptr"):                # torch tensor on the ctx's GPU
+            n = leaf_hashes.numel() // 32
+            _abi.check(self._lib.afc_merkle_tree_build_dev(self.ctx.handle, _abi.ptr(leaf_hashes), n, C.byref(h)), self.ctx.handle)
+        else:
+            lh = np.ascontiguousarray(leaf_hashes, dtype=np.uint8).reshape(-1, 32)
+            n = lh.shape[0]
+            _abi.check(self._lib.afc_merkle_tree_build(self.ctx.handle, _abi.ptr(lh) if n else None, n, C.byref(h)), self.ctx.handle)
+        self.handle, self.n = h, n
+        root = np.zeros(32, dtype=np.uint8)
+        nl, depth = C.c_uint64(), C.c_uint32()
+        _abi.check(self._lib.afc_merkle_tree_root(self.handle, _abi.ptr(root), C.byref(nl), C.byref(depth)), self.ctx.handle)
+        self.root, self.depth = root.tobytes(), depth.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.afc_merkle_tree_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def inclusion_proofs(self, indices):
+        """-> list of audit paths (each a list of 32-byte nodes, leaf-to-root order, RFC 6962 §2.1.1)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        m = idx.shape[0]
+        out = np.zeros((m, self.depth, 32), dtype=np.uint8)
+        lens = np.zeros(m, dtype=np.uint32)
+        _abi.check(self._lib.afc_merkle_tree_inclusion_proofs(self.handle, _abi.ptr(idx), m, _abi.ptr(out), _abi.ptr(lens)), self.ctx.handle)
+        return [[out[i, k].tobytes() for k in range(int(lens[i]))] for i in range(m)]
+
+
+def verify_inclusion_batch(leaf_hashes, indices, tree_size, proofs, root, ctx=None):
+    """Bulk offline audit: ok[i] = path i leads from leaf_hashes[i] at position indices[i] to `root` (RFC 9162 §2.1.3.2)."""
+    ctx = ctx or default_context()
+    lib = _abi.load()
+    if isinstance(leaf_hashes, (list, tuple)):
+        leaf_hashes = np.frombuffer(b"".join(leaf_hashes), dtype=np.uint8)
+    lh = np.ascontiguousarray(leaf_hashes, dtype=np.uint8).reshape(-1, 32).copy()
+    m = lh.shape[0]
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    off = np.zeros(m + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(p) for p in proofs])
+    flat = np.frombuffer(b"".join(b"".join(p) for p in proofs), dtype=np.uint8).copy() if off[-1] else np.zeros(32, dtype=np.uint8)
+    rt = np.frombuffer(root, dtype=np.uint8).copy()
+    ok = np.zeros(m, dtype=np.uint8)
+    _abi.check(lib.afc_merkle_verify_inclusion_batch(ctx.handle, _abi.ptr(lh), _abi.ptr(idx), tree_size, _abi.ptr(flat), _abi.ptr(off), _abi.ptr(rt), m,
+                                                     _abi.ptr(ok)), ctx.handle)
+    return ok.astype(bool)

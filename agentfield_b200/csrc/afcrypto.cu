@@ -99,6 +99,15 @@ struct afc_keyset {
     size_t tab_bytes = 0;
 };
 
+struct afc_merkle_tree {
+    afc_ctx* ctx = nullptr;
+    uint64_t n = 0;
+    std::vector<uint8_t*> levels;        // device pointers, level 0 = leaf hashes
+    std::vector<uint64_t> sizes;
+    uint8_t** d_levels = nullptr;        // the same table on the device
+    uint64_t* d_sizes = nullptr;
+};
+
 struct afc_merkle {
     afc_ctx* ctx = nullptr;
     uint64_t size = 0;
@@ -750,6 +759,123 @@ int afc_merkle_load(afc_merkle* m, const uint8_t* state) {
     CK(cudaStreamSynchronize(m->stream));
     memcpy(&m->size, state, 8);
     CK(cudaMemcpy(m->d_frontier, state + 8, 64 * 32, cudaMemcpyHostToDevice));
+    return AFC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------- materialised tree + audit proofs
+static int tree_build_common(afc_ctx* ctx, const uint8_t* src, bool src_is_device, uint64_t n, afc_merkle_tree** out) {
+    if (!ctx || !out || (n && !src)) return AFC_EINVAL;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    afc_merkle_tree* t = new (std::nothrow) afc_merkle_tree();
+    if (!t) return AFC_ENOMEM;
+    t->ctx = ctx; t->n = n;
+    CallLog lc(ctx, 72);
+    cudaError_t e = cudaSuccess;
+    uint64_t cur = n;
+    while (e == cudaSuccess) {
+        uint8_t* p = nullptr;
+        e = cudaMalloc((void**)&p, (size_t)(cur ? cur : 1) * 32);
+        if (e != cudaSuccess) break;
+        t->levels.push_back(p); t->sizes.push_back(cur);
+        size_t h = t->levels.size() - 1;
+        if (h == 0) {
+            if (n) e = cudaMemcpy(p, src, (size_t)n * 32, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+        } else {
+            e = launch::merkle_level_promote(t->levels[h - 1], t->sizes[h - 1], p, 0, lc);
+        }
+        if (cur <= 1) break;
+        cur = (cur + 1) / 2;
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&t->d_levels, t->levels.size() * sizeof(uint8_t*));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&t->d_sizes, t->sizes.size() * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(t->d_levels, t->levels.data(), t->levels.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t->d_sizes, t->sizes.data(), t->sizes.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_err(ctx, e, "afc_merkle_tree_build"); afc_merkle_tree_free(t); return e == cudaErrorMemoryAllocation ? AFC_ENOMEM : AFC_ECUDA; }
+    *out = t;
+    return AFC_OK;
+}
+int afc_merkle_tree_build(afc_ctx* ctx, const uint8_t* leaf_hashes32, uint64_t n, afc_merkle_tree** out) { return tree_build_common(ctx, leaf_hashes32, false, n, out); }
+int afc_merkle_tree_build_dev(afc_ctx* ctx, const uint8_t* d_leaf_hashes32, uint64_t n, afc_merkle_tree** out) { return tree_build_common(ctx, d_leaf_hashes32, true, n, out); }
+void afc_merkle_tree_free(afc_merkle_tree* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    for (uint8_t* p : t->levels) if (p) cudaFree(p);
+    if (t->d_levels) cudaFree(t->d_levels);
+    if (t->d_sizes) cudaFree(t->d_sizes);
+    delete t;
+}
+int afc_merkle_tree_root(afc_merkle_tree* t, uint8_t root32[32], uint64_t* n_leaves, uint32_t* max_proof_nodes) {
+    if (!t) return AFC_EINVAL;
+    afc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (n_leaves) *n_leaves = t->n;
+    if (max_proof_nodes) *max_proof_nodes = (uint32_t)(t->levels.size() > 1 ? t->levels.size() - 1 : 1);
+    if (root32) {
+        if (t->n == 0) {                                   // MTH({}) = SHA-256("") — computed on the device like everything else
+            CallLog lc(ctx);
+            uint8_t* d = nullptr;
+            CK(cudaMalloc((void**)&d, 32));
+            cudaError_t e = launch::merkle_root(d, 0, d, 0, lc);
+            if (e == cudaSuccess) e = cudaMemcpy(root32, d, 32, cudaMemcpyDeviceToHost);
+            cudaFree(d);
+            CK(e);
+        } else {
+            CK(cudaMemcpy(root32, t->levels.back(), 32, cudaMemcpyDeviceToHost));
+        }
+    }
+    return AFC_OK;
+}
+int afc_merkle_tree_inclusion_proofs(afc_merkle_tree* t, const uint64_t* indices, uint32_t m, uint8_t* proofs, uint32_t* proof_lens) {
+    if (!t || (m && (!indices || !proofs || !proof_lens))) return AFC_EINVAL;
+    afc_ctx* ctx = t->ctx;
+    if (m == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < m; i++) if (indices[i] >= t->n) return AFC_EINVAL;
+    const size_t depth = t->levels.size() > 1 ? t->levels.size() - 1 : 1;
+    uint64_t* d_idx = nullptr; uint8_t* d_out = nullptr; uint32_t* d_len = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_idx, (size_t)m * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)m * depth * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_len, (size_t)m * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_idx, indices, (size_t)m * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        CallLog lc(ctx);
+        e = launch::merkle_gather_proofs((const uint8_t* const*)t->d_levels, t->d_sizes, (int)t->levels.size(), d_idx, m, d_out, d_len, 0, lc);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(proofs, d_out, (size_t)m * depth * 32, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(proof_lens, d_len, (size_t)m * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_idx); cudaFree(d_out); cudaFree(d_len);
+    CK(e);
+    return AFC_OK;
+}
+int afc_merkle_verify_inclusion_batch(afc_ctx* ctx, const uint8_t* leaf_hashes32, const uint64_t* indices, uint64_t tree_size,
+                                      const uint8_t* proofs, const uint32_t* proof_off, const uint8_t root32[32], uint32_t m, uint8_t* ok) {
+    if (!ctx || (m && (!leaf_hashes32 || !indices || !proof_off || !root32 || !ok))) return AFC_EINVAL;
+    if (m == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t pn = proof_off[m];
+    if (pn && !proofs) return AFC_EINVAL;
+    uint8_t *d_lh = nullptr, *d_pr = nullptr, *d_root = nullptr, *d_ok = nullptr; uint64_t* d_idx = nullptr; uint32_t* d_po = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_lh, (size_t)m * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_pr, (pn ? pn : 1) * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_root, 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_ok, m);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_idx, (size_t)m * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_po, (size_t)(m + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_lh, leaf_hashes32, (size_t)m * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && pn) e = cudaMemcpy(d_pr, proofs, pn * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_root, root32, 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_idx, indices, (size_t)m * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_po, proof_off, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        CallLog lc(ctx);
+        e = launch::merkle_verify_inclusion(d_lh, d_idx, tree_size, d_pr, d_po, d_root, m, d_ok, 0, lc);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(ok, d_ok, m, cudaMemcpyDeviceToHost);
+    cudaFree(d_lh); cudaFree(d_pr); cudaFree(d_root); cudaFree(d_ok); cudaFree(d_idx); cudaFree(d_po);
+    CK(e);
     return AFC_OK;
 }
 

@@ -263,22 +263,8 @@ __global__ void k_microbench_fe(int which, uint32_t iters, uint32_t* sink) {
     } else if (which == 27) { probe_mix<0, 3>(iters, a, b);
     } else if (which == 28) { probe_mix<16, 3>(iters, a, b);
     } else if (which == 29) { probe_mix<48, 0>(iters, a, b);
-    } else if (which == 10) {
-        // raw pipe probes (2 * 8 instructions per iteration): 8 independent IMAD.WIDE.U32 accumulators
-        uint64_t acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = ((uint64_t)a.v[i] << 32) | b.v[i];
-        uint32_t m0 = a.v[0] | 1, m1 = b.v[1] | 1;
-        for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = (uint64_t)m0 * (uint32_t)(m1 + i) + acc[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) { a.v[i] ^= (uint32_t)acc[i]; b.v[i] ^= (uint32_t)(acc[i] >> 32); }
     } else if (which == 11) {
-        // 16 IMAD (32-bit) per iteration
+        // raw pipe probes: 16 dependent 32-bit IMAD per iteration (8 independent chains)
         uint32_t acc[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] = a.v[i];
@@ -304,28 +290,6 @@ __global__ void k_microbench_fe(int which, uint32_t iters, uint32_t* sink) {
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) a.v[i] ^= acc[i];
-    } else if (which == 13) {
-        // 8 IMAD.WIDE + 8 carry-chain adds per iteration (both pipes)
-        uint64_t acc[4];
-        uint32_t s[8];
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[i] = ((uint64_t)a.v[i] << 32) | b.v[i];
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = b.v[i];
-        uint32_t m0 = a.v[0] | 1, m1 = b.v[1] | 1;
-        for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) acc[i] = (uint64_t)m0 * (uint32_t)(m1 + i) + acc[i];
-#pragma unroll
-                for (int i = 0; i < 4; i++) s[2 * r + i] = (s[2 * r + i] + a.v[i]) ^ (s[(i + 5) & 7] & 0x55555555u);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { a.v[i] ^= (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32); }
-#pragma unroll
-        for (int i = 0; i < 8; i++) b.v[i] ^= s[i];
     } else {
         for (uint32_t it = 0; it < iters; it++) { fe_mul(a, a, a); fe_mul(b, b, b); }
     }

@@ -109,6 +109,87 @@ __global__ void k_merkle_root(const uint8_t* __restrict__ frontier, uint64_t siz
 }
 
 
+
+// ---- materialised tree for audit proofs: every level kept, unpaired last node promoted unchanged
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_level_promote(const uint8_t* __restrict__ in, uint64_t n_in, uint8_t* __restrict__ out) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t npairs = n_in >> 1;
+    if (p < npairs) {
+        uint32_t l[8], r[8], o[8];
+        load_node(l, in + 64 * p);
+        load_node(r, in + 64 * p + 32);
+        sha256_merkle_node(o, l, r);
+        store_digest256(out + 32 * p, o);
+    } else if (p == npairs && (n_in & 1)) {
+        const uint4* src = (const uint4*)(in + 32 * (n_in - 1));
+        uint4 a = src[0], b = src[1];
+        uint4* dst = (uint4*)(out + 32 * npairs);
+        dst[0] = a; dst[1] = b;
+    }
+}
+
+// RFC 6962 §2.1.1 audit paths for many leaves at once: one thread per requested index walks the stored levels.
+// levels[h] = device pointer to level h (32-byte nodes), sizes[h] = node count; out: m x depth x 32, lens: m.
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_gather_proofs(const uint8_t* const* __restrict__ levels, const uint64_t* __restrict__ sizes, int n_levels,
+                       const uint64_t* __restrict__ indices, uint32_t m, uint8_t* __restrict__ out, uint32_t* __restrict__ lens) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    uint64_t idx = indices[t];
+    uint8_t* o = out + (size_t)t * (n_levels > 1 ? n_levels - 1 : 1) * 32;
+    uint32_t k = 0;
+    if (idx < sizes[0]) {
+        for (int h = 0; h + 1 < n_levels; h++) {
+            uint64_t sib = idx ^ 1;
+            if (sib < sizes[h]) {
+                const uint4* src = (const uint4*)(levels[h] + 32 * sib);
+                uint4 a = src[0], b = src[1];
+                uint4* dst = (uint4*)(o + 32 * k);
+                dst[0] = a; dst[1] = b;
+                k++;
+            }
+            idx >>= 1;
+        }
+    }
+    lens[t] = k;
+}
+
+// RFC 9162 §2.1.3.2 inclusion verification, one proof per thread.  leaf_hashes: m x 32; proofs packed, proof_off[m+1] in
+// units of 32-byte nodes; ok[i] = 1 iff the path leads to `root` for (indices[i], tree_size).
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_verify_inclusion(const uint8_t* __restrict__ leaf_hashes, const uint64_t* __restrict__ indices, uint64_t tree_size,
+                          const uint8_t* __restrict__ proofs, const uint32_t* __restrict__ proof_off, const uint8_t* __restrict__ root,
+                          uint32_t m, uint8_t* __restrict__ ok) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    uint64_t fn = indices[t], sn = tree_size - 1;
+    uint32_t good = (tree_size != 0) && (fn < tree_size);
+    uint32_t r[8], want[8];
+    load_node(r, leaf_hashes + 32ull * t);
+    load_node(want, root);
+    if (good) {
+        for (uint32_t k = proof_off[t]; k < proof_off[t + 1]; k++) {
+            if (sn == 0) { good = 0; break; }
+            uint32_t p[8], o[8];
+            load_node(p, proofs + 32ull * k);
+            if ((fn & 1) || fn == sn) {
+                sha256_merkle_node(o, p, r);
+                if (!(fn & 1)) { while (fn && !(fn & 1)) { fn >>= 1; sn >>= 1; } }
+            } else {
+                sha256_merkle_node(o, r, p);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = o[i];
+            fn >>= 1; sn >>= 1;
+        }
+    }
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) diff |= r[i] ^ want[i];
+    ok[t] = (uint8_t)(good && sn == 0 && diff == 0);
+}
+
 // ---- text codecs either side of the kernels: base64url without padding for signatures / digests
 // (base64.RawURLEncoding in vc_service.go:465,514) and lowercase hex for the webhook header (hex.EncodeToString,
 // webhook_dispatcher.go:473).  Fixed-size records; one thread per 3-byte group / per byte pair.
@@ -195,6 +276,22 @@ cudaError_t merkle_level(const uint8_t* in, uint8_t* out, uint64_t npairs, int l
 }
 cudaError_t merkle_root(const uint8_t* frontier, uint64_t size, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
     AFC_LAUNCH(lg, "k_merkle_root", s, k_merkle_root<<<1, 32, 0, s>>>(frontier, size, out32));
+    return cudaGetLastError();
+}
+cudaError_t merkle_level_promote(const uint8_t* in, uint64_t n_in, uint8_t* out, cudaStream_t s, LaunchLog* lg) {
+    AFC_LAUNCH(lg, "k_merkle_level_promote", s, k_merkle_level_promote<<<blocks_for((n_in >> 1) + 1, HASH_THREADS), HASH_THREADS, 0, s>>>(in, n_in, out));
+    return cudaGetLastError();
+}
+cudaError_t merkle_gather_proofs(const uint8_t* const* levels, const uint64_t* sizes, int n_levels, const uint64_t* indices, uint32_t m,
+                                 uint8_t* out, uint32_t* lens, cudaStream_t s, LaunchLog* lg) {
+    if (m == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_merkle_gather_proofs", s, k_merkle_gather_proofs<<<blocks_for(m, HASH_THREADS), HASH_THREADS, 0, s>>>(levels, sizes, n_levels, indices, m, out, lens));
+    return cudaGetLastError();
+}
+cudaError_t merkle_verify_inclusion(const uint8_t* leaf_hashes, const uint64_t* indices, uint64_t tree_size, const uint8_t* proofs,
+                                    const uint32_t* proof_off, const uint8_t* root, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg) {
+    if (m == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_merkle_verify_inclusion", s, k_merkle_verify_inclusion<<<blocks_for(m, HASH_THREADS), HASH_THREADS, 0, s>>>(leaf_hashes, indices, tree_size, proofs, proof_off, root, m, ok));
     return cudaGetLastError();
 }
 cudaError_t b64url_encode(const uint8_t* in, uint32_t item, uint32_t n, uint8_t* out, cudaStream_t s, LaunchLog* lg) {

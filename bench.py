@@ -430,8 +430,7 @@ def extras(ctx, dev, world, rank):
     mb = {}
     for name, which, iters in (("fe_mul", 0, 4000), ("fe_sq", 1, 4000), ("fe_addsub", 2, 20000), ("fe_mul_portable", 5, 2000),
                                ("fe_sq_via_mul", 6, 4000), ("fe_mul_schoolbook", 7, 4000), ("sha256_compress", 3, 2000), ("sha512_compress", 4, 1000),
-                               ("pipe_imad_wide_x16", 10, 20000), ("pipe_imad32_x16", 11, 20000), ("pipe_alu_x16", 12, 20000),
-                               ("pipe_mix_wide8_alu8", 13, 20000),
+                               ("pipe_imad32_x16", 11, 20000), ("pipe_alu_x16", 12, 20000),
                                ("probe_w8_a0", 20, 20000), ("probe_w8_a8", 21, 20000), ("probe_w8_a16", 22, 20000), ("probe_w8_a24", 23, 20000),
                                ("probe_w8_a32", 24, 20000), ("probe_w8_a48", 29, 20000), ("probe_w8_carrypairs16", 25, 20000),
                                ("probe_w8_xor16", 26, 20000), ("probe_wX8_a0", 27, 20000), ("probe_wX8_a16", 28, 20000)):

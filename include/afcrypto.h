@@ -149,6 +149,21 @@ int afc_merkle_load(afc_merkle* m, const uint8_t* state);
 int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n,
                                uint8_t* d_out32, void* stream);
 
+/* ---- N4: audit proofs for bulk offline verification (`af vc verify`, internal/cli/vc.go:159-331; export bundles,
+ * internal/handlers/ui/did.go:533-865) ------------------------------------------------------------------------
+ * afc_merkle_tree materialises every level over a fixed set of leaf hashes (device memory, ~2n x 32 B) so that RFC 6962
+ * §2.1.1 audit paths can be read out in bulk; afc_merkle_verify_inclusion_batch checks many paths against one root on
+ * the device (RFC 9162 §2.1.3.2).  proof_off: m+1 offsets in units of 32-byte nodes. */
+typedef struct afc_merkle_tree afc_merkle_tree;
+int afc_merkle_tree_build(afc_ctx* ctx, const uint8_t* leaf_hashes32, uint64_t n, afc_merkle_tree** out);
+int afc_merkle_tree_build_dev(afc_ctx* ctx, const uint8_t* d_leaf_hashes32, uint64_t n, afc_merkle_tree** out);
+void afc_merkle_tree_free(afc_merkle_tree* t);
+int afc_merkle_tree_root(afc_merkle_tree* t, uint8_t root32[32], uint64_t* n_leaves, uint32_t* max_proof_nodes);
+int afc_merkle_tree_inclusion_proofs(afc_merkle_tree* t, const uint64_t* indices, uint32_t m, uint8_t* proofs /* m x max_proof_nodes x 32 */,
+                                     uint32_t* proof_lens /* m, in nodes */);
+int afc_merkle_verify_inclusion_batch(afc_ctx* ctx, const uint8_t* leaf_hashes32, const uint64_t* indices, uint64_t tree_size,
+                                      const uint8_t* proofs, const uint32_t* proof_off, const uint8_t root32[32], uint32_t m, uint8_t* ok);
+
 /* ---- multi-GPU: independent shards, one exchange step --------------------------------
  * Each rank appends its contiguous, 2^k-aligned leaf range to its own afc_merkle; the 32-byte subtree
  * roots are all-gathered (NCCL over NVLink) and every rank folds the top levels redundantly.

@@ -380,6 +380,31 @@ def test_device_resident_variants_equal_host_variants(ctx):
     assert torch.equal(d_sigs, d_sigs2)
 
 
+def test_merkle_audit_proofs_match_rfc6962(ctx):
+    """N4: audit paths read out of the materialised tree == the recursive RFC 6962 definition; bulk verification accepts them and
+    rejects a wrong leaf, a wrong index, a truncated path and a wrong root."""
+    from agentfield_b200 import MerkleTree, verify_inclusion_batch, Auditor
+    rng = np.random.default_rng(0xAF44)
+    for n in (1, 2, 3, 7, 8, 100, 1000, 4097):
+        hs = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(n)]
+        t = MerkleTree(np.frombuffer(b"".join(hs), dtype=np.uint8), ctx)
+        assert t.root == OM.root_from_leaf_hashes(hs)
+        a = Auditor(ctx); assert a.append_hashes(np.frombuffer(b"".join(hs), dtype=np.uint8))[0] == t.root; a.close()
+        idx = sorted({0, n - 1, n // 2, n // 3, min(n - 1, 5)})
+        proofs = t.inclusion_proofs(idx)
+        for m, p in zip(idx, proofs):
+            assert p == OM.inclusion_proof(hs, m), (n, m)
+            assert OM.verify_inclusion(hs[m], m, n, p, t.root)
+        ok = verify_inclusion_batch([hs[m] for m in idx], idx, n, proofs, t.root, ctx)
+        assert ok.all(), n
+        if n > 3:
+            assert not verify_inclusion_batch([hs[(m + 1) % n] for m in idx], idx, n, proofs, t.root, ctx).any()
+            assert not verify_inclusion_batch([hs[m] for m in idx], [(m + 1) % n for m in idx], n, proofs, t.root, ctx).all()
+            assert not verify_inclusion_batch([hs[m] for m in idx], idx, n, [p[:-1] for p in proofs], t.root, ctx).any()
+            assert not verify_inclusion_batch([hs[m] for m in idx], idx, n, proofs, bytes(32), ctx).any()
+        t.close()
+
+
 def test_device_text_codecs(ctx):
     """base64url (no padding) and lowercase hex of fixed-size records == Go's base64.RawURLEncoding / hex.EncodeToString."""
     import base64
