@@ -30,6 +30,23 @@ AFC_HD uint32_t maj32(uint32_t x, uint32_t y, uint32_t z) { return (x & y) ^ (x 
 #define AFC_OUTLINE static __device__ __noinline__
 #endif
 
+// ALU-pipe relief: the SHA-256 kernels are bound by the ALU pipe (shifts, LOP3, IADD3: ncu 84-91 % busy) while the FMA pipe
+// idles.  A two-input add written as a * ONE + b with ONE read from the constant bank is emitted as an IMAD and executes on
+// the FMA pipe instead (the compiler cannot fold a __constant__ operand).  AFC_SHA_IMAD_ADDS selects how many adds move.
+#ifndef AFC_SHA_IMAD_ADDS
+#define AFC_SHA_IMAD_ADDS 1
+#endif
+#if defined(AFC_HOSTSIM)
+#define AFC_FADD(a, b) ((a) + (b))
+#else
+static __device__ __constant__ uint32_t AFC_ONE = 1u;
+#if AFC_SHA_IMAD_ADDS
+#define AFC_FADD(a, b) ((a) * AFC_ONE + (b))
+#else
+#define AFC_FADD(a, b) ((a) + (b))
+#endif
+#endif
+
 // One compression: st += F(st, w[0..15]).  Fully unrolled (round constants become constant-bank immediates, the
 // schedule window stays in registers); ONE out-of-line copy per kernel, state and block passed in registers.
 struct sha256_io { uint32_t st[8]; uint32_t w[16]; };
@@ -42,11 +59,18 @@ AFC_OUTLINE sha256_st sha256_compress_regs(sha256_io x) {
             uint32_t w15 = x.w[(i - 15) & 15], w2 = x.w[(i - 2) & 15];
             uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
             uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-            x.w[i & 15] = x.w[i & 15] + s0 + x.w[(i - 7) & 15] + s1;
+            x.w[i & 15] = AFC_FADD(AFC_FADD(x.w[i & 15], x.w[(i - 7) & 15]), s0 + s1);
         }
-        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g) + AFC_K256[i] + x.w[i & 15];
+        uint32_t hk = AFC_FADD(AFC_FADD(h, x.w[i & 15]), AFC_K256[i]);           // off the critical path: FMA pipe
+#if AFC_SHA_IMAD_ADDS >= 2
+        uint32_t t1 = AFC_FADD(AFC_FADD(hk, rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)), ch32(e, f, g));
+        uint32_t t2 = AFC_FADD(rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22), maj32(a, b, c));
+        h = g; g = f; f = e; e = AFC_FADD(d, t1); d = c; c = b; b = a; a = AFC_FADD(t1, t2);
+#else
+        uint32_t t1 = hk + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ch32(e, f, g);
         uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + maj32(a, b, c);
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        h = g; g = f; f = e; e = AFC_FADD(d, t1); d = c; c = b; b = a; a = t1 + t2;
+#endif
     }
     sha256_st r;
     r.st[0] = x.st[0] + a; r.st[1] = x.st[1] + b; r.st[2] = x.st[2] + c; r.st[3] = x.st[3] + d;

@@ -48,10 +48,12 @@ k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, con
     store_words8((uint8_t*)(k_out + 8ull * i), k);
 }
 
-// Variants (selected with AFC_VERIFY_VARIANT, default 0 = inline; measured 29.7 ms vs 31.3 ms per 1 M on B200) differ only in how field multiplications are emitted and in the
+// Variants (AFC_VERIFY_VARIANT: 0 = inline multiplies, 249 registers, 2 CTAs/SM — default, 27.2 ms per 1 M on B200;
+// 1 = out-of-line multiplies, 140 registers, 3 CTAs/SM — 28.8 ms).  Also measured and dropped: inline at 168 registers
+// with 128/96/64-thread CTAs (28.6 / 31.9 / 29.3 ms: spills), inline 64-thread CTAs at 249 registers (27.2 ms, no gain). differ only in how field multiplications are emitted and in the
 // register budget: F = FeCall keeps the loop I-cache resident; MINB blocks/SM bounds registers (2 -> 255, 3 -> 168, 4 -> 128).
-template <class F, int MINB>
-__global__ void __launch_bounds__(ED_THREADS, MINB)
+template <class F, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs,
             const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
     __shared__ ge_precomp sB[COMB_COLS];         // (j+1)B, j = 0..127: 12 KB, staged with 128-bit loads
@@ -318,8 +320,8 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
     const ge_precomp* cb = (const ge_precomp*)comb;
     const uint32_t nb = blocks_for(n, ED_THREADS);
     switch (variant) {
-    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 3><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
-    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 2><<<nb, ED_THREADS, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 128, 3><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 128, 2><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
     }
     return cudaGetLastError();
 }

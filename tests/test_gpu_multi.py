@@ -78,3 +78,41 @@ def test_merkle_root_allgather_and_round_robin_two_gpus():
     for rank, f1, f2, full, okc, expc in res:
         assert f1 == full and f2 == full, rank
         assert okc == expc
+
+
+def test_single_process_drives_several_gpus():
+    """How the Go control plane uses the library (SURVEY.md §8e "Replicas"): ONE process, one afc_ctx per device, batches
+    dealt round-robin from concurrent threads, results scattered back by index."""
+    import threading
+    import torch
+    import agentfield_b200 as afb
+    from oracle import c_oracle as CO
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs 2 GPUs")
+    ctxs = [afb.Context(d) for d in range(g)]
+    rng = np.random.default_rng(0xAF66)
+    n = 6000
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, (n, 512), dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * 512
+    sigs = CO.ed25519_sign_batch(seeds, msgs.reshape(-1), off, 8)
+    sigs[::4, 7] ^= 1
+    pks = CO.ed25519_pubkey_batch(seeds, 8)
+    expect = CO.ed25519_verify_batch(pks, sigs, msgs.reshape(-1), off, 8)
+    ok = np.zeros(n, dtype=np.uint8)
+    batch = 500
+
+    def worker(d):
+        for b0 in range(d * batch, n, g * batch):            # batch i -> GPU i mod G
+            b1 = min(n, b0 + batch)
+            o = np.arange(b1 - b0 + 1, dtype=np.uint64) * 512
+            ok[b0:b1] = ctxs[d].verify_packed(pks[b0:b1].copy(), sigs[b0:b1].copy(), msgs[b0:b1].reshape(-1).copy(), o)
+    ts = [threading.Thread(target=worker, args=(d,)) for d in range(g)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert (ok == expect).all() and ok.sum() == n - len(range(0, n, 4))
+    for c in ctxs:
+        c.close()

@@ -348,6 +348,39 @@ def test_ingest_soak_sustains_target_rate(ctx):
     ing.close()
 
 
+def test_concurrent_callers_share_one_context(ctx):
+    """The C ABI is thread-safe and re-entrant (reference callers are concurrent goroutines, one per HTTP request;
+    webhook_dispatcher.go:118-121 runs 4 workers): 8 threads hammer one afc_ctx with different operations."""
+    import threading
+    rng = np.random.default_rng(0xAF55)
+    n = 3000
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, (n, 300), dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * 300
+    exp_sig = CO.ed25519_sign_batch(seeds, msgs.reshape(-1), off, 8)
+    exp_dig = CO.sha256_batch(msgs.reshape(-1), off, 8)
+    pks = CO.ed25519_pubkey_batch(seeds, 8)
+    errs = []
+
+    def work(t):
+        try:
+            for rep in range(3):
+                if t % 3 == 0:
+                    assert (ctx.sign_packed(seeds, msgs.reshape(-1), off) == exp_sig).all()
+                elif t % 3 == 1:
+                    assert ctx.verify_packed(pks, exp_sig, msgs.reshape(-1), off).all()
+                else:
+                    assert (ctx.sha256_packed(msgs.reshape(-1), off) == exp_dig).all()
+        except Exception as e:     # noqa: BLE001
+            errs.append((t, repr(e)))
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
 # ----------------------------------------------------------------------------- device-pointer (resident) variants
 def test_device_resident_variants_equal_host_variants(ctx):
     import torch
