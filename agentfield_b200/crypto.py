@@ -85,6 +85,15 @@ class Context:
         _abi.check(self._lib.afc_microbench(self.handle, which, iters, C.byref(ops), C.byref(ms)), self.handle)
         return ops.value, ms.value
 
+    def keycache_configure(self, max_keys):
+        """Capacity of the transparent issuer-key cache behind verify (0 disables it: always the generic kernel)."""
+        _abi.check(self._lib.afc_keycache_configure(self.handle, int(max_keys)), self.handle)
+
+    def keycache_info(self):
+        mk, ck, md = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _abi.check(self._lib.afc_keycache_info(self.handle, C.byref(mk), C.byref(ck), C.byref(md)), self.handle)
+        return {"max_keys": mk.value, "cached_keys": ck.value, "last_mode": md.value}
+
     def profile_begin(self, max_launches=4096):
         _abi.check(self._lib.afc_profile_begin(self.handle, max_launches), self.handle)
 

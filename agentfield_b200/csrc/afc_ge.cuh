@@ -255,10 +255,29 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
     ge_cached c;
     ge_p3_to_cached<F>(c, P);
     M = P;
+    // 128 consecutive multiples, converted to affine 16 at a time with ONE field inversion per chunk (Montgomery's trick):
+    // 8 inversions per row instead of 128.
+    constexpr int CH = 16;
+    fe d2; fe_const(d2, AFC_D2_32);
 #pragma unroll 1
-    for (int j = 0; j < COMB_COLS; j++) {
-        ge_p3_to_precomp<F>(row[j], M);
-        ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
+    for (int c0 = 0; c0 < COMB_COLS; c0 += CH) {
+        fe X[CH], Y[CH], Z[CH], Pz[CH];                  // thread-local scratch (2 KB)
+#pragma unroll 1
+        for (int j = 0; j < CH; j++) {
+            fe_copy(X[j], M.X); fe_copy(Y[j], M.Y); fe_copy(Z[j], M.Z);
+            if (j == 0) fe_copy(Pz[0], M.Z); else F::mul(Pz[j], Pz[j - 1], M.Z);
+            ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
+        }
+        fe inv; fe_invert<F>(inv, Pz[CH - 1]);           // 1 / (Z_0 ... Z_15)
+#pragma unroll 1
+        for (int j = CH - 1; j >= 0; j--) {
+            fe zi;
+            if (j > 0) { F::mul(zi, inv, Pz[j - 1]); F::mul(inv, inv, Z[j]); } else fe_copy(zi, inv);
+            fe x, y, xy;
+            F::mul(x, X[j], zi); F::mul(y, Y[j], zi);
+            ge_precomp& r = row[c0 + j];
+            fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); F::mul(xy, x, y); F::mul(r.xy2d, xy, d2);
+        }
     }
     return ok;
 }

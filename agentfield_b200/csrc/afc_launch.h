@@ -59,9 +59,24 @@ cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t
 // comb: 32 x 128 ge_precomp (row 0 = the 128 small multiples of B)
 size_t ed_tables_bytes();
 cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg);
-// scratch_k: n * 32 bytes
+// Device buffers of the transparent issuer-key cache used by ed_verify_batch (see k_ed25519.cu); owned by afcrypto.cu.
+struct KeyCache {
+    uint32_t* slots;        // persistent open-addressing table: slot -> cache id, 0xffffffff = empty   (slot_mask + 1 entries)
+    uint32_t slot_mask;
+    uint32_t max_keys;
+    uint8_t* cpks;          // max_keys x 32
+    uint8_t* valid;         // max_keys
+    void* tabs;             // max_keys x 32 x 128 ge_precomp
+    uint32_t* state;        // 8 words: [0] cached keys [1] mode [2] reset pending [3] distinct [4] to build [5] snapshot [6] missing
+    uint32_t* build_list;   // max_keys
+    uint32_t* bslots;       // per-call: batch de-duplication table (bmask + 1 entries, >= 2n)
+    uint32_t bmask;
+    uint32_t* rep;          // per-call: n
+    uint32_t* kid;          // per-call: n
+};
+// scratch_k: n * 32 bytes; kc: nullable (nullptr = always the generic Straus kernel)
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
-                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
+                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, const KeyCache* kc, cudaStream_t s, LaunchLog* lg);
 size_t ed_key_table_bytes(uint32_t n_keys);
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,

@@ -77,6 +77,13 @@ struct afc_ctx {
     std::condition_variable cv;
     std::atomic<unsigned long long> launches{0};
     std::string last_error;
+    // transparent issuer-key cache behind afc_ed25519_verify_batch (see k_ed25519.cu)
+    launch::KeyCache kc{};
+    bool kc_ready = false;
+    uint32_t kc_max_keys = 1024;        // AFC_KEYCACHE_MAX_KEYS / afc_keycache_configure; 0 disables
+    uint32_t kc_call_cap = 0;           // per-call scratch capacity (items)
+    std::mutex kc_mu;
+    cudaEvent_t kc_event = nullptr;     // orders successive users of the cache across streams
     // per-kernel CUDA-event profiling (afc_profile_begin / afc_profile_end)
     bool profile = false;
     std::vector<launch::LaunchRec> prof_recs;
@@ -150,6 +157,57 @@ struct CallLog {
     }
     operator launch::LaunchLog*() { return &lg; }
 };
+
+
+// ---- issuer-key cache management ------------------------------------------------------------------------------
+void kc_free(afc_ctx* ctx) {
+    launch::KeyCache& k = ctx->kc;
+    void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.state, k.build_list, k.bslots, k.rep, k.kid};
+    for (void* p : ps) if (p) cudaFree(p);
+    k = launch::KeyCache{};
+    ctx->kc_ready = false; ctx->kc_call_cap = 0;
+}
+// Makes the cache usable for a call of n items (allocating / growing as needed).  Returns nullptr when disabled or when
+// memory cannot be had — callers then run the generic kernel.  Caller holds kc_mu.
+const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
+    if (ctx->kc_max_keys == 0 || n < 64) return nullptr;
+    launch::KeyCache& k = ctx->kc;
+    if (!ctx->kc_ready) {
+        uint32_t cap = 1; while (cap < 4 * ctx->kc_max_keys) cap <<= 1;
+        k.slot_mask = cap - 1; k.max_keys = ctx->kc_max_keys;
+        bool ok = cudaMalloc((void**)&k.slots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.cpks, (size_t)k.max_keys * 32) == cudaSuccess &&
+                  cudaMalloc((void**)&k.valid, k.max_keys) == cudaSuccess && cudaMalloc(&k.tabs, launch::ed_key_table_bytes(k.max_keys)) == cudaSuccess &&
+                  cudaMalloc((void**)&k.state, 8 * 4) == cudaSuccess && cudaMalloc((void**)&k.build_list, (size_t)k.max_keys * 4) == cudaSuccess &&
+                  cudaMemset(k.slots, 0xff, (size_t)cap * 4) == cudaSuccess && cudaMemset(k.state, 0, 8 * 4) == cudaSuccess &&
+                  cudaMemset(k.valid, 0, k.max_keys) == cudaSuccess &&
+                  (ctx->kc_event || cudaEventCreateWithFlags(&ctx->kc_event, cudaEventDisableTiming) == cudaSuccess);
+        if (!ok) { cudaGetLastError(); kc_free(ctx); ctx->kc_max_keys = 0; return nullptr; }     // no room: stay generic
+        ctx->kc_ready = true;
+    }
+    if (n > ctx->kc_call_cap) {
+        if (k.bslots) cudaFree(k.bslots);
+        if (k.rep) cudaFree(k.rep);
+        if (k.kid) cudaFree(k.kid);
+        k.bslots = k.rep = k.kid = nullptr;
+        uint32_t want = n + n / 4;
+        uint32_t cap = 1; while (cap < 2 * (uint64_t)want && cap < 0x80000000u) cap <<= 1;
+        bool ok = cudaMalloc((void**)&k.bslots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.rep, (size_t)want * 4) == cudaSuccess &&
+                  cudaMalloc((void**)&k.kid, (size_t)want * 4) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); ctx->kc_call_cap = 0; return nullptr; }
+        k.bmask = cap - 1; ctx->kc_call_cap = want;
+    }
+    return &k;
+}
+// verify through the cache when possible; serialises cache users across streams with an event
+cudaError_t verify_with_cache(afc_ctx* ctx, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                              uint8_t* ok, uint32_t* scratch_k, cudaStream_t st, launch::LaunchLog* lg) {
+    std::lock_guard<std::mutex> g(ctx->kc_mu);
+    const launch::KeyCache* kc = kc_prepare(ctx, n);
+    if (kc) { cudaError_t e = cudaStreamWaitEvent(st, ctx->kc_event, 0); if (e != cudaSuccess) return e; }
+    cudaError_t e = launch::ed_verify_batch(ctx->comb, pks, sigs, msgs, off, n, ok, scratch_k, kc, st, lg);
+    if (kc && e == cudaSuccess) e = cudaEventRecord(ctx->kc_event, st);
+    return e;
+}
 
 struct LaneGuard {
     afc_ctx* ctx; int idx;
@@ -276,7 +334,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
             break;
         }
         case OP_VERIFY:
-            e = launch::ed_verify_batch(ctx->comb, sl.a.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
+            e = verify_with_cache(ctx, sl.a.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
             break;
         case OP_VERIFY_KEYED: {
             CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used));
@@ -337,6 +395,7 @@ int afc_init(int device, afc_ctx** out) {
     afc_ctx* ctx = new (std::nothrow) afc_ctx();
     if (!ctx) return AFC_ENOMEM;
     ctx->device = device;
+    if (const char* e = getenv("AFC_KEYCACHE_MAX_KEYS")) ctx->kc_max_keys = (uint32_t)strtoul(e, nullptr, 10);
     auto fail = [&](cudaError_t e, const char* what) { set_err(ctx, e, what); fprintf(stderr, "afc_init: %s\n", ctx->last_error.c_str()); afc_destroy(ctx); return AFC_ECUDA; };
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
@@ -364,6 +423,8 @@ void afc_destroy(afc_ctx* ctx) {
             sl.msgs.release(); sl.off.release(); sl.a.release(); sl.b.release(); sl.k.release(); sl.out.release(); sl.koff.release();
             sl.h_in.release(); sl.h_out.release();
         }
+    kc_free(ctx);
+    if (ctx->kc_event) cudaEventDestroy(ctx->kc_event);
     if (ctx->comb) cudaFree(ctx->comb);
     for (auto& r : ctx->prof_recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
     delete ctx;
@@ -475,7 +536,7 @@ int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8
     // k scratch: per-call allocation from the stream-ordered pool (freed in stream order)
     uint32_t* d_k = nullptr;
     if (n) CK(cudaMallocAsync((void**)&d_k, (size_t)n * 32, st));
-    cudaError_t e = launch::ed_verify_batch(ctx->comb, d_pks, d_sigs, d_msgs, d_msg_off, n, d_ok, d_k, st, lc);
+    cudaError_t e = verify_with_cache(ctx, d_pks, d_sigs, d_msgs, d_msg_off, n, d_ok, d_k, st, lc);
     if (n) cudaFreeAsync(d_k, st);
     CK(e);
     DEV_EPILOGUE();
@@ -525,6 +586,28 @@ int afc_hex_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_by
     if (n && item_bytes && (!d_in || !d_out)) return AFC_EINVAL;
     CK(launch::hex_encode(d_in, (uint64_t)item_bytes * n, d_out, st, lc));
     DEV_EPILOGUE();
+}
+
+
+int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys) {
+    if (!ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->kc_mu);
+    CK(cudaDeviceSynchronize());
+    kc_free(ctx);
+    ctx->kc_max_keys = max_keys;
+    return AFC_OK;
+}
+int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode) {
+    if (!ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->kc_mu);
+    uint32_t st[8] = {0};
+    if (ctx->kc_ready) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(st, ctx->kc.state, sizeof st, cudaMemcpyDeviceToHost)); }
+    if (max_keys) *max_keys = ctx->kc_max_keys;
+    if (cached_keys) *cached_keys = st[0];
+    if (last_mode) *last_mode = st[1];
+    return AFC_OK;
 }
 
 // ---------------------------------------------------------------------------------- keyed verification

@@ -55,7 +55,8 @@ k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, con
 template <class F, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs,
-            const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
+            const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok, const uint32_t* __restrict__ skip_if_set) {
+    if (skip_if_set && *skip_if_set) return;    // the table-driven kernel handled this batch (uniform across the grid)
     __shared__ ge_precomp sB[COMB_COLS];         // (j+1)B, j = 0..127: 12 KB, staged with 128-bit loads
     {
         const uint4* src = (const uint4*)comb;
@@ -117,6 +118,127 @@ k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restr
     load_words8(sig + 8, sigs + 64ull * i + 32);
     load_words8(k, (const uint8_t*)(ks + 8ull * i));
     ok[i] = (uint8_t)ed25519_verify_keyed_core<FeInline>(pk_ok, sig, k, tabs + (size_t)key * COMB_ROWS * COMB_COLS, comb);
+}
+
+
+// ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
+// Issuers repeat: the reference verifies against the DIDs its own registry derived (vc_service.go:259), BASELINE's
+// configs[1] draws 10^6 credentials from 1024 keys.  The generic entry point therefore (1) de-duplicates the batch's public
+// keys in a device hash table, (2) looks the distinct keys up in a persistent per-context cache of radix-256 tables,
+// (3) decides ON THE DEVICE whether amortised table building pays (new keys x ~48 verify-equivalents <= batch size and the
+// cache has room), builds the missing tables and (4) runs either the table-driven kernel or the generic Straus kernel —
+// the other one exits immediately.  No host synchronisation; results are bit-identical either way.
+using KeyCacheDev = launch::KeyCache;     // POD descriptor of the device buffers (afc_launch.h)
+constexpr uint32_t KC_EMPTY = 0xffffffffu;
+constexpr uint32_t KC_AMORTISE = 48;      // one table costs about this many generic verifications
+
+__device__ __forceinline__ uint32_t kc_hash(const uint32_t* w) {
+    uint32_t h = w[0] * 0x9E3779B1u ^ w[1];
+    h = (h ^ (h >> 15)) * 0x85EBCA77u ^ w[2];
+    h = (h ^ (h >> 13)) * 0xC2B2AE3Du ^ w[5];
+    return h ^ (h >> 16);
+}
+__device__ __forceinline__ bool kc_equal(const uint32_t* a, const uint8_t* p) {
+    uint32_t b[8];
+    load_words8(b, p);
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+    return d == 0;
+}
+
+__global__ void k_kc_begin(KeyCacheDev kc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        kc.state[1] = 0; kc.state[3] = 0; kc.state[4] = 0; kc.state[6] = 0;
+        kc.state[5] = kc.state[0];
+    }
+}
+// pass 1: in-batch de-duplication; representatives also probe the persistent cache (lookup only)
+__global__ void __launch_bounds__(256)
+k_kc_dedup(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    load_words8(w, pks + 32ull * i);
+    uint32_t h0 = kc_hash(w), h = h0 & kc.bmask;
+    uint32_t r = i;
+    for (;;) {
+        uint32_t cur = kc.bslots[h];
+        if (cur == KC_EMPTY) {
+            cur = atomicCAS(&kc.bslots[h], KC_EMPTY, i);
+            if (cur == KC_EMPTY) break;                       // i is the representative
+        }
+        if (kc_equal(w, pks + 32ull * cur)) { r = cur; break; }
+        h = (h + 1) & kc.bmask;
+    }
+    kc.rep[i] = r;
+    if (r != i) return;
+    atomicAdd(&kc.state[3], 1u);
+    // persistent lookup
+    uint32_t id = KC_EMPTY, cached = kc.state[5];
+    h = h0 & kc.slot_mask;
+    for (uint32_t probes = 0; probes <= kc.slot_mask; probes++) {
+        uint32_t cur = kc.slots[h];
+        if (cur == KC_EMPTY) break;
+        if (cur < cached && kc_equal(w, kc.cpks + 32ull * cur)) { id = cur; break; }
+        h = (h + 1) & kc.slot_mask;
+    }
+    kc.kid[i] = id;
+    if (id == KC_EMPTY) atomicAdd(&kc.state[6], 1u);
+}
+__global__ void k_kc_mode(KeyCacheDev kc, uint32_t n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t cached = kc.state[5], distinct = kc.state[3], missing = kc.state[6];
+    uint32_t build = missing, reset = 0;
+    if (cached + missing > kc.max_keys) { reset = 1; build = distinct; }      // does not fit next to what is cached: start over
+    bool keyed = build <= kc.max_keys && (uint64_t)build * KC_AMORTISE <= n;
+    kc.state[1] = keyed ? 1u : 0u;
+    kc.state[2] = (keyed && reset) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+k_kc_reset(KeyCacheDev kc) {
+    if (!kc.state[2]) return;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t s = t; s <= kc.slot_mask; s += gridDim.x * blockDim.x) kc.slots[s] = KC_EMPTY;
+    if (t == 0) { kc.state[0] = 0; kc.state[5] = 0; }
+}
+// pass 2 (table-driven mode only): representatives not yet cached claim an id, publish their key and queue a build
+__global__ void __launch_bounds__(256)
+k_kc_insert(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !kc.state[1] || kc.rep[i] != i) return;
+    if (kc.state[2]) kc.kid[i] = KC_EMPTY;                    // cache was reset: earlier ids are void
+    if (kc.kid[i] != KC_EMPTY) return;
+    uint32_t w[8];
+    load_words8(w, pks + 32ull * i);
+    uint32_t id = atomicAdd(&kc.state[0], 1u);               // cannot exceed max_keys: k_kc_mode checked
+    store_words8(kc.cpks + 32ull * id, w);
+    uint32_t h = kc_hash(w) & kc.slot_mask;
+    while (atomicCAS(&kc.slots[h], KC_EMPTY, id) != KC_EMPTY) h = (h + 1) & kc.slot_mask;   // distinct keys: no equality test needed
+    kc.kid[i] = id;
+    kc.build_list[atomicAdd(&kc.state[4], 1u)] = id;
+}
+__global__ void __launch_bounds__(ED_THREADS)
+k_kc_build(KeyCacheDev kc) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!kc.state[1] || t >= kc.state[4] * COMB_ROWS) return;
+    uint32_t id = kc.build_list[t / COMB_ROWS], row = t % COMB_ROWS;
+    uint32_t pk[8];
+    load_words8(pk, kc.cpks + 32ull * id);
+    int ok = ge_build_key_row<FeCall>((ge_precomp*)kc.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS, pk, (int)row);
+    if (row == 0) kc.valid[id] = (uint8_t)ok;
+}
+__global__ void __launch_bounds__(ED_THREADS, 3)
+k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
+                   uint32_t n, uint8_t* __restrict__ ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !kc.state[1]) return;
+    uint32_t id = kc.kid[kc.rep[i]];
+    uint32_t sig[16], k[8];
+    load_words8(sig, sigs + 64ull * i);
+    load_words8(sig + 8, sigs + 64ull * i + 32);
+    load_words8(k, (const uint8_t*)(ks + 8ull * i));
+    ok[i] = (uint8_t)ed25519_verify_keyed_core<FeInline>((int)kc.valid[id], sig, k, (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS, comb);
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
@@ -312,20 +434,37 @@ cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
     return cudaGetLastError();
 }
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
-                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
+                            uint32_t n, uint8_t* ok, uint32_t* scratch_k, const KeyCache* kcp, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
-    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("AFC_VERIFY_VARIANT"); variant = e ? atoi(e) : 0; }
     const ge_precomp* cb = (const ge_precomp*)comb;
     const uint32_t nb = blocks_for(n, ED_THREADS);
+    const uint32_t* skip = nullptr;
+    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+    if (kcp) {
+        // issuer-key cache: de-duplicate, look up, decide on the device, build what is missing, verify through tables
+        const KeyCache kc = *kcp;
+        cudaError_t e = cudaMemsetAsync(kc.bslots, 0xff, ((size_t)kc.bmask + 1) * 4, s);
+        if (e != cudaSuccess) return e;
+        AFC_LAUNCH(lg, "k_kc_begin", s, k_kc_begin<<<1, 32, 0, s>>>(kc));
+        AFC_LAUNCH(lg, "k_kc_dedup", s, k_kc_dedup<<<blocks_for(n, 256), 256, 0, s>>>(kc, pks, n));
+        AFC_LAUNCH(lg, "k_kc_mode", s, k_kc_mode<<<1, 32, 0, s>>>(kc, n));
+        AFC_LAUNCH(lg, "k_kc_reset", s, k_kc_reset<<<64, 256, 0, s>>>(kc));
+        AFC_LAUNCH(lg, "k_kc_insert", s, k_kc_insert<<<blocks_for(n, 256), 256, 0, s>>>(kc, pks, n));
+        // at most min(max_keys, n / KC_AMORTISE) tables can be due in one call
+        uint64_t max_build = kc.max_keys < n / KC_AMORTISE ? kc.max_keys : n / KC_AMORTISE;
+        if (max_build)
+            AFC_LAUNCH(lg, "k_kc_build", s, k_kc_build<<<blocks_for(max_build * COMB_ROWS, ED_THREADS), ED_THREADS, 0, s>>>(kc));
+        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<nb, ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, ok));
+        skip = kc.state + 1;
+    }
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("AFC_VERIFY_VARIANT"); variant = e ? atoi(e) : 0; }
     switch (variant) {
-    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 128, 3><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
-    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 128, 2><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok)); break;
+    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 128, 3><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok, skip)); break;
+    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 128, 2><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok, skip)); break;
     }
     return cudaGetLastError();
 }
-
 size_t ed_key_table_bytes(uint32_t n_keys) { return sizeof(ge_precomp) * (size_t)n_keys * COMB_ROWS * COMB_COLS; }
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg) {
     if (n_keys == 0) return cudaSuccess;

@@ -83,6 +83,15 @@ int afc_ed25519_verify_batch(afc_ctx* ctx, const uint8_t* pks, const uint8_t* si
 int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_sigs, const uint8_t* d_msgs,
                                  const uint64_t* d_msg_off, uint32_t n, uint8_t* d_ok, void* stream);
 
+/* Transparent issuer-key cache behind afc_ed25519_verify_batch[_dev]: the batch's public keys are de-duplicated on the
+ * device, looked up in a persistent per-context cache of per-key tables (384 KB per key), missing tables are built when
+ * that pays for itself (new keys x ~48 verify-equivalents <= batch size and the cache has room; a full cache is reset), and
+ * the table-driven kernel runs instead of the generic one.  Decisions are taken on the device, nothing synchronises, results
+ * are bit-identical.  max_keys = 0 disables (always the generic kernel); default 1024, or env AFC_KEYCACHE_MAX_KEYS.
+ * afc_keycache_info: cached_keys = tables currently held, last_mode = 1 if the last verify call went through tables. */
+int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys);
+int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode);
+
 /* ---- N1: keyed verification (the identity cache) ---------------------------------------------------------
  * The reference resolves every issuer DID from its own registry before it verifies (VCService.VerifyVC,
  * internal/services/vc_service.go:259 -> DIDService.ResolveDID, internal/services/did_service.go:368-473) and the

@@ -251,6 +251,62 @@ def test_keyed_verify_equals_generic_verify_and_go_rules(ctx):
     ks.close()
 
 
+def test_transparent_key_cache_paths(ctx):
+    """afc_ed25519_verify_batch with the issuer-key cache: every decision path must give the oracle's bitmap — distinct keys
+    (generic kernel), repeated keys (tables built, then reused), cache overflow (reset + rebuild), more distinct keys than the
+    cache holds (generic), Go-rule edge keys through the table path, and cache disabled."""
+    rng = np.random.default_rng(0xAF77)
+
+    def batch(nk, n, seed_off=0, msg_len=200):
+        seeds = np.random.default_rng(1000 + seed_off).integers(0, 256, (nk, 32), dtype=np.uint8)
+        kp = ctx.pubkeys(seeds)
+        ki = rng.integers(0, nk, n)
+        msgs = rng.integers(0, 256, (n, msg_len), dtype=np.uint8)
+        off = np.arange(n + 1, dtype=np.uint64) * msg_len
+        sigs = ctx.sign_packed(seeds[ki].copy(), msgs.reshape(-1), off)
+        sigs[::13, 4] ^= 8
+        pks = kp[ki].copy()
+        pks[5::2500, 2] ^= 1                                 # a few corrupted (mostly off-curve / unknown) keys
+        return pks, sigs, msgs.reshape(-1), off
+
+    def check(args, want_mode=None):
+        pks, sigs, buf, off = args
+        got = ctx.verify_packed(pks, sigs, buf, off)
+        assert (got == CO.ed25519_verify_batch(pks, sigs, buf, off, 8)).all()
+        info = ctx.keycache_info()
+        if want_mode is not None:
+            assert info["last_mode"] == want_mode, info
+        return info
+
+    try:
+        ctx.keycache_configure(16)
+        check(batch(3000, 3000, 1), want_mode=0)             # ~all keys distinct: generic kernel
+        i1 = check(batch(10, 6000, 2), want_mode=1)          # 10 keys (+ a few corrupted ones), heavy reuse
+        assert 10 <= i1["cached_keys"] <= 16
+        b = batch(10, 6000, 2)
+        b[0][5::2500, 2] ^= 1                                 # same 10 keys, no corrupted ones this time
+        i2 = check(b, want_mode=1)                            # reuse: nothing new to build
+        assert i2["cached_keys"] == i1["cached_keys"]
+        i3 = check(batch(12, 9000, 3), want_mode=1)          # 12 other keys do not fit next to the cached ones: reset + rebuild
+        assert i3["cached_keys"] <= 16
+        check(batch(40, 20000, 4), want_mode=0)              # 40 hot keys > capacity 16: generic kernel
+        ctx.keycache_configure(256)
+        es = golden("ed25519_edge.json")
+        rep = 120
+        pks = np.frombuffer(b"".join(bytes.fromhex(e["pk"]) for e in es) * rep, dtype=np.uint8).reshape(-1, 32).copy()
+        sigs = np.frombuffer(b"".join(bytes.fromhex(e["sig"]) for e in es) * rep, dtype=np.uint8).reshape(-1, 64).copy()
+        from agentfield_b200 import pack
+        buf, off = pack([bytes.fromhex(e["msg"]) for e in es] * rep)
+        got = ctx.verify_packed(pks, sigs, buf, off)
+        assert ctx.keycache_info()["last_mode"] == 1
+        assert (got.reshape(rep, -1) == np.array([e["valid"] for e in es], dtype=np.uint8)).all()
+        ctx.keycache_configure(0)
+        check(batch(10, 6000, 5), want_mode=0)
+        assert ctx.keycache_info()["max_keys"] == 0
+    finally:
+        ctx.keycache_configure(1024)
+
+
 def test_expanded_key_cache_derivation_matches_reference_flow(ctx):
     from agentfield_b200 import ExpandedKeys
     g = golden("reference_flow.json")
