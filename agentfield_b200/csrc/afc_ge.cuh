@@ -171,9 +171,35 @@ AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* co
     }
 }
 
+// Canonical encodings of G projective points with ONE field inversion (Montgomery's trick).  Every Z must be non-zero
+// (true for any point on the curve: the a = -1 twisted Edwards addition law is complete).
+template <class F, int G>
+AFC_HD void ge_encode_many(uint32_t (*enc)[8], const fe* X, const fe* Y, const fe* Z) {
+    fe pz[G];
+    fe_copy(pz[0], Z[0]);
+#pragma unroll
+    for (int g = 1; g < G; g++) F::mul(pz[g], pz[g - 1], Z[g]);
+    fe inv; fe_invert<F>(inv, pz[G - 1]);
+#pragma unroll
+    for (int g = G - 1; g >= 0; g--) {
+        fe zi;
+        if (g > 0) { F::mul(zi, inv, pz[g - 1]); F::mul(inv, inv, Z[g]); } else fe_copy(zi, inv);
+        fe x, y;
+        F::mul(x, X[g], zi); F::mul(y, Y[g], zi);
+        fe_towords(enc[g], y);
+        enc[g][7] |= (uint32_t)fe_isnegative(x) << 31;
+    }
+}
+
+// Go's checks that do not involve the curve: sig[63] & 224 == 0 and S canonical
+AFC_HD int ed25519_sig_wellformed(const uint32_t* sig) { return !(sig[15] & 0xE0000000u) && sc_is_canonical(sig + 8); }
+
 // ---------------------------------------------------------------------------------- verify core
 // pk, sig: little-endian words of the given byte strings; k = SHA-512(R || A || M) mod L.
 // Returns 1 iff Go's ed25519.Verify would return true.
+// Returns 1 iff Go's ed25519.Verify would return true.  (A split into point + shared-inversion finish, as the table-driven
+// kernels use, was measured on this kernel and dropped: ptxas allocates 172 instead of 249 registers and the Straus loop runs
+// 14 % slower.)
 template <class F = FeInline>
 AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const uint32_t* k, const ge_precomp* b128) {
     int ok = 1;
@@ -282,12 +308,10 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
     return ok;
 }
 
-// pk_ok: the key decoded; atab: that key's 32 x 128 table of -A; comb: the base-point table.
+// R' = [S]B + [k](-A) through the two radix-256 tables, left in projective form (X : Y : Z).
+// atab: that key's 32 x 128 table of -A; comb: the base-point table.
 template <class F = FeInline>
-AFC_HD int ed25519_verify_keyed_core(int pk_ok, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* comb) {
-    int ok = pk_ok;
-    if (sig[15] & 0xE0000000u) ok = 0;
-    if (!sc_is_canonical(sig + 8)) ok = 0;
+AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* comb) {
     uint32_t kt[8], st[8];
     sc_recode256(kt, k);
     sc_recode256(st, sig + 8);
@@ -296,6 +320,14 @@ AFC_HD int ed25519_verify_keyed_core(int pk_ok, const uint32_t* sig, const uint3
 #pragma unroll 1
     for (int i = 0; i < 32; i++) {
         int dk = sc_digit256(kt, i), ds = sc_digit256(st, i);
+#if AFC_DEVICE_CODE
+        if (i + 1 < 32) {       // the next row's two entries are random 96-byte reads (HBM / L2): start them now
+            int nk = sc_digit256(kt, i + 1), ns = sc_digit256(st, i + 1);
+            int mk = nk < 0 ? -nk : nk, ms = ns < 0 ? -ns : ns;
+            if (mk) { const char* p = (const char*)&atab[(i + 1) * COMB_COLS + (mk - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+            if (ms) { const char* p = (const char*)&comb[(i + 1) * COMB_COLS + (ms - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+        }
+#endif
         if (dk != 0) {
             int neg = dk < 0, m = neg ? -dk : dk;
             ge_maddsub<F>(t, h, atab[i * COMB_COLS + (m - 1)], neg);
@@ -307,12 +339,21 @@ AFC_HD int ed25519_verify_keyed_core(int pk_ok, const uint32_t* sig, const uint3
             ge_p1p1_to_p3<F>(h, t);
         }
     }
-    uint32_t enc[8];
-    ge_encode<F>(enc, h.X, h.Y, h.Z);
+    fe_copy(X, h.X); fe_copy(Y, h.Y); fe_copy(Z, h.Z);
+}
+
+// pk_ok: the key decoded.  Single-credential form (used by the key-set kernel and the CPU checks).
+template <class F = FeInline>
+AFC_HD int ed25519_verify_keyed_core(int pk_ok, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* comb) {
+    fe X, Y, Z;
+    ed25519_keyed_point<F>(X, Y, Z, sig, k, atab, comb);
+    uint32_t enc[1][8];
+    if (!pk_ok) { fe_0(X); fe_1(Y); fe_1(Z); }          // garbage table: keep the arithmetic well defined, result is forced to 0
+    ge_encode_many<F, 1>(enc, &X, &Y, &Z);
     uint32_t diff = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) diff |= enc[i] ^ sig[i];
-    return ok & (diff == 0);
+    for (int i = 0; i < 8; i++) diff |= enc[0][i] ^ sig[i];
+    return (pk_ok != 0) & ed25519_sig_wellformed(sig) & (diff == 0);
 }
 
 // k = SHA-512(R || A || M) mod L

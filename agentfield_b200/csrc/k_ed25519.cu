@@ -74,8 +74,11 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
     ok[i] = (uint8_t)ed25519_verify_core<F>(pk, sig, k, sB);
 }
 
-
 // ---- keyed verification (identity cache): per-key radix-256 tables of -A, built once per key set
+#ifndef AFC_KC_GROUP
+#define AFC_KC_GROUP 4
+#endif
+constexpr int KC_GROUP = AFC_KC_GROUP;   // credentials per thread in the table-driven kernels (one shared field inversion)
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_key_rows(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_precomp* __restrict__ tabs, uint8_t* __restrict__ valid) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,19 +110,39 @@ __global__ void __launch_bounds__(ED_THREADS, 3)
 k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                   const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
                   const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t key = key_index[i];
-    int pk_ok = key < n_keys;
-    if (!pk_ok) key = 0;
-    pk_ok &= (int)valid[key];
-    uint32_t sig[16], k[8];
-    load_words8(sig, sigs + 64ull * i);
-    load_words8(sig + 8, sigs + 64ull * i + 32);
-    load_words8(k, (const uint8_t*)(ks + 8ull * i));
-    ok[i] = (uint8_t)ed25519_verify_keyed_core<FeInline>(pk_ok, sig, k, tabs + (size_t)key * COMB_ROWS * COMB_COLS, comb);
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((uint64_t)t * KC_GROUP >= n) return;
+    fe X[KC_GROUP], Y[KC_GROUP], Z[KC_GROUP];
+    uint32_t good = 0;
+#pragma unroll 1
+    for (int g = 0; g < KC_GROUP; g++) {
+        uint32_t i = t * KC_GROUP + g;
+        fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
+        if (i >= n) continue;
+        uint32_t key = key_index[i];
+        if (key >= n_keys || !valid[key]) continue;          // unknown index or undecodable key: ok = 0
+        uint32_t sig[16], k[8];
+        load_words8(sig, sigs + 64ull * i);
+        load_words8(sig + 8, sigs + 64ull * i + 32);
+        load_words8(k, (const uint8_t*)(ks + 8ull * i));
+        if (!ed25519_sig_wellformed(sig)) continue;
+        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, tabs + (size_t)key * COMB_ROWS * COMB_COLS, comb);
+        good |= 1u << g;
+    }
+    uint32_t enc[KC_GROUP][8];
+    ge_encode_many<FeInline, KC_GROUP>(enc, X, Y, Z);
+#pragma unroll 1
+    for (int g = 0; g < KC_GROUP; g++) {
+        uint32_t i = t * KC_GROUP + g;
+        if (i >= n) break;
+        uint32_t r[8];
+        load_words8(r, sigs + 64ull * i);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
+        ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
+    }
 }
-
 
 // ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
 // Issuers repeat: the reference verifies against the DIDs its own registry derived (vc_service.go:259), BASELINE's
@@ -228,17 +251,45 @@ k_kc_build(KeyCacheDev kc) {
     int ok = ge_build_key_row<FeCall>((ge_precomp*)kc.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS, pk, (int)row);
     if (row == 0) kc.valid[id] = (uint8_t)ok;
 }
+// (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
+// the register allocation of the curve loop around and nothing overlaps that did not already.)
+// Each thread handles KC_GROUP consecutive credentials and shares ONE field inversion between their final encodings
+// (Montgomery's trick): the inversion is a quarter of this kernel's multiplier work when done per credential.
 __global__ void __launch_bounds__(ED_THREADS, 3)
 k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
                    uint32_t n, uint8_t* __restrict__ ok) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !kc.state[1]) return;
-    uint32_t id = kc.kid[kc.rep[i]];
-    uint32_t sig[16], k[8];
-    load_words8(sig, sigs + 64ull * i);
-    load_words8(sig + 8, sigs + 64ull * i + 32);
-    load_words8(k, (const uint8_t*)(ks + 8ull * i));
-    ok[i] = (uint8_t)ed25519_verify_keyed_core<FeInline>((int)kc.valid[id], sig, k, (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS, comb);
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((uint64_t)t * KC_GROUP >= n || !kc.state[1]) return;
+    fe X[KC_GROUP], Y[KC_GROUP], Z[KC_GROUP];
+    uint32_t good = 0;
+#pragma unroll 1
+    for (int g = 0; g < KC_GROUP; g++) {
+        uint32_t i = t * KC_GROUP + g;
+        fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
+        if (i >= n) continue;
+        uint32_t id = kc.kid[kc.rep[i]];
+        if (!kc.valid[id]) continue;                         // key does not decode: ok = 0, arithmetic skipped
+        uint32_t sig[16], k[8];
+        load_words8(sig, sigs + 64ull * i);
+        load_words8(sig + 8, sigs + 64ull * i + 32);
+        load_words8(k, (const uint8_t*)(ks + 8ull * i));
+        if (!ed25519_sig_wellformed(sig)) continue;
+        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS, comb);
+        good |= 1u << g;
+    }
+    uint32_t enc[KC_GROUP][8];
+    ge_encode_many<FeInline, KC_GROUP>(enc, X, Y, Z);
+#pragma unroll 1
+    for (int g = 0; g < KC_GROUP; g++) {
+        uint32_t i = t * KC_GROUP + g;
+        if (i >= n) break;
+        uint32_t r[8];
+        load_words8(r, sigs + 64ull * i);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
+        ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
+    }
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
@@ -454,7 +505,7 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         uint64_t max_build = kc.max_keys < n / KC_AMORTISE ? kc.max_keys : n / KC_AMORTISE;
         if (max_build)
             AFC_LAUNCH(lg, "k_kc_build", s, k_kc_build<<<blocks_for(max_build * COMB_ROWS, ED_THREADS), ED_THREADS, 0, s>>>(kc));
-        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<nb, ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, ok));
+        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(((uint64_t)n + KC_GROUP - 1) / KC_GROUP, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, ok));
         skip = kc.state + 1;
     }
     static int variant = -1;
@@ -476,7 +527,7 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
                                   uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
-    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok));
+    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(((uint64_t)n + KC_GROUP - 1) / KC_GROUP, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok));
     return cudaGetLastError();
 }
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,

@@ -615,3 +615,39 @@ def test_full_size_merkle_config4_single_gpu(ctx):
             b.close()
         assert fold_roots(np.frombuffer(b"".join(roots), dtype=np.uint8), ctx) == root
         a.close()
+
+
+def test_full_size_config4_sign_4M_and_merkle_append(ctx):
+    """cfg4 at full size on one GPU: 4 194 304 (2^22) and 4 000 000 credentials of 512 B signed with 1 024 cached keys, every
+    signature verified back (table path), signatures appended as audit leaves; the root equals the oracle's RFC 6962 root over
+    the same signatures, and a 20 000-signature sample equals the oracle's signatures byte for byte."""
+    import torch
+    from agentfield_b200 import Auditor
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xAF04)
+    K = 1024
+    rng = np.random.default_rng(0xAF04)
+    kseeds = rng.integers(0, 256, (K, 32), dtype=np.uint8)
+    d_exp = torch.empty((K, 96), dtype=torch.uint8, device=dev)
+    ctx.expand_dev(torch.from_numpy(kseeds).to(dev), K, d_exp)
+    for n in (1 << 22, 4_000_000):
+        d_msgs = torch.randint(0, 256, (n, 512), dtype=torch.uint8, device=dev, generator=g)
+        d_off = torch.arange(n + 1, device=dev, dtype=torch.int64) * 512
+        d_ki = (torch.arange(n, device=dev) % K).to(torch.int32)
+        d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        ctx.sign_expanded_dev(d_exp, d_ki, d_msgs.view(-1), d_off, n, d_sigs)
+        d_pks = d_exp[:, 64:][d_ki.long()].contiguous()
+        d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
+        ctx.verify_dev(d_pks, d_sigs, d_msgs.view(-1), d_off, n, d_ok)
+        a = Auditor(ctx)
+        a.append_dev(d_sigs.view(-1), torch.arange(n + 1, device=dev, dtype=torch.int64) * 64, n)
+        root, size = a.root()
+        torch.cuda.synchronize()
+        assert size == n and bool(d_ok.all())
+        sig_h = d_sigs.cpu().numpy()
+        assert CO.merkle_root(sig_h.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 64, 8) == root
+        m = 20_000
+        exp = CO.ed25519_sign_batch(kseeds[np.arange(m) % K].copy(), d_msgs[:m].cpu().numpy().reshape(-1), np.arange(m + 1, dtype=np.uint64) * 512, 8)
+        assert (sig_h[:m] == exp).all()
+        a.close()
+        del d_msgs, d_sigs, d_pks, d_ok
