@@ -48,6 +48,7 @@ SYMBOLS = {
     "afc_ed25519_sign_expanded_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_keycache_configure": (C.c_int, [vp, C.c_uint32]),
     "afc_keycache_info": (C.c_int, [vp, u32p, u32p, u32p]),
+    "afc_keycache_clear": (C.c_int, [vp, vp]),
     "afc_keyset_new": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
     "afc_keyset_free": (None, [vp]),
     "afc_keyset_info": (C.c_int, [vp, u32p, u64p]),

@@ -89,6 +89,10 @@ class Context:
         """Capacity of the transparent issuer-key cache behind verify (0 disables it: always the generic kernel)."""
         _abi.check(self._lib.afc_keycache_configure(self.handle, int(max_keys)), self.handle)
 
+    def keycache_clear(self, stream=None):
+        """Forget every cached table (stream-ordered; device memory is kept)."""
+        _abi.check(self._lib.afc_keycache_clear(self.handle, self._stream(stream)), self.handle)
+
     def keycache_info(self):
         mk, ck, md = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _abi.check(self._lib.afc_keycache_info(self.handle, C.byref(mk), C.byref(ck), C.byref(md)), self.handle)

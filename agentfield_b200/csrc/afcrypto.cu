@@ -598,6 +598,18 @@ int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys) {
     ctx->kc_max_keys = max_keys;
     return AFC_OK;
 }
+int afc_keycache_clear(afc_ctx* ctx, void* stream) {
+    if (!ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->kc_mu);
+    if (!ctx->kc_ready) return AFC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamWaitEvent(st, ctx->kc_event, 0));
+    CK(cudaMemsetAsync(ctx->kc.slots, 0xff, ((size_t)ctx->kc.slot_mask + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->kc.state, 0, 8 * 4, st));
+    CK(cudaEventRecord(ctx->kc_event, st));
+    return AFC_OK;
+}
 int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode) {
     if (!ctx) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));

@@ -91,6 +91,8 @@ int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8
  * afc_keycache_info: cached_keys = tables currently held, last_mode = 1 if the last verify call went through tables. */
 int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys);
 int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode);
+/* forget every cached table (stream-ordered: enqueued on `stream`, ordered after earlier verify calls); memory is kept */
+int afc_keycache_clear(afc_ctx* ctx, void* stream);
 
 /* ---- N1: keyed verification (the identity cache) ---------------------------------------------------------
  * The reference resolves every issuer DID from its own registry before it verifies (VCService.VerifyVC,
