@@ -8,11 +8,13 @@ A "step" is one pass of the hot path over one batch: per GPU, configs[1] of BASE
 1 M x 512 B credentials (K = 1024 key pairs, 1 % corrupted so the kernel cannot short-circuit).  Weak
 scaling: every rank verifies its own 1 M batch, no collective on the data path (§8e).
 
-  value      verifies/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  value      verifies/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).  Every step starts from
+             an EMPTY issuer-key cache: de-duplication, the 1024 per-key tables and all 10^6 verifications happen inside the step
   e2e        the same work through the C-ABI host call (afc_ed25519_verify_batch): pinned host buffers, H2D of all inputs and
-             D2H of the result bitmap inside the timed region
-  roofline   the dominant kernel (k_ed_verify) against the measured HBM peak, algorithmic bytes = 609 B / credential
+             D2H of the result bitmap inside the timed region (cache emptied before every step as well)
+  roofline   the dominant kernel against the measured HBM peak, algorithmic bytes = 609 B / credential
   cpu_baseline  the oracle's C port of Go's algorithm on this box's host cores, bounded sample (rank 0, N = 1 only)
+  warm_keycache / no_keycache / keyed   secondary figures: tables kept between steps, cache disabled (generic kernel), explicit key set
 
 Only the `cpu_baseline` leg and `--impl reference` execute anything under oracle/.
 """
@@ -317,7 +319,7 @@ def main():
     traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of k_ed_verify from the committed ncu --set full capture (same 1 M launch)
         tk = json.load(open(os.path.join(ROOT, "profiles", "r01_e_ncu_traffic.json")))["kernels"]
-        traffic = tk.get(dom, tk.get("k_ed_verify_keyed" if dom == "k_ed_verify_cached" else dom, {})).get("traffic_bytes")
+        traffic = tk.get(dom, {}).get("traffic_bytes")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -98,3 +98,11 @@ def test_ed25519_kernel_logic_vs_golden_and_oracle(hostsim):
         assert hostsim.hs_verify(pk, m, C.c_uint64(len(m)), s) == 1
         bs = bytearray(s); bs[i % 64] ^= 1 << (i % 8)
         assert hostsim.hs_verify(pk, m, C.c_uint64(len(m)), bytes(bs)) == 0
+
+
+def test_keyed_table_path_logic_vs_golden(hostsim):
+    """Per-key radix-256 table build (chunked Montgomery inversion) + table-driven verification, on the CPU build."""
+    es = golden("ed25519_edge.json") + [dict(e, valid=True) for e in golden("rfc8032.json")]
+    for e in es:
+        pk, msg, sig = (bytes.fromhex(e[k]) for k in ("pk", "msg", "sig"))
+        assert hostsim.hs_verify_keyed(pk, msg, C.c_uint64(len(msg)), sig) == int(e["valid"]), e["name"]
