@@ -71,6 +71,8 @@ SYMBOLS = {
     "afc_merkle_tree_root": (C.c_int, [vp, vp, u64p, u32p]),
     "afc_merkle_tree_inclusion_proofs": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
     "afc_merkle_verify_inclusion_batch": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp]),
+    "afc_merkle_tree_consistency_proof": (C.c_int, [vp, C.c_uint64, vp, u32p]),
+    "afc_merkle_verify_consistency_batch": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp]),
     "afc_comm_unique_id": (C.c_int, [vp]),
     "afc_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "afc_comm_allgather_roots": (C.c_int, [vp, vp, vp]),

@@ -139,6 +139,31 @@ class MerkleTree:
         _abi.check(self._lib.afc_merkle_tree_inclusion_proofs(self.handle, _abi.ptr(idx), m, _abi.ptr(out), _abi.ptr(lens)), self.ctx.handle)
         return [[out[i, k].tobytes() for k in range(int(lens[i]))] for i in range(m)]
 
+    def consistency_proof(self, first):
+        """-> RFC 6962 §2.1.2 proof (list of 32-byte nodes) that this tree extends the tree of its first `first` leaves."""
+        out = np.zeros((2 * max(self.depth, 1) + 2, 32), dtype=np.uint8)
+        k = C.c_uint32()
+        _abi.check(self._lib.afc_merkle_tree_consistency_proof(self.handle, int(first), _abi.ptr(out), C.byref(k)), self.ctx.handle)
+        return [out[i].tobytes() for i in range(k.value)]
+
+
+def verify_consistency_batch(first_sizes, first_roots, second_size, second_root, proofs, ctx=None):
+    """Bulk check that the log at (second_size, second_root) extends each earlier checkpoint (first_sizes[i], first_roots[i])
+    (RFC 9162 §2.1.4.2); proofs[i] = list of 32-byte nodes (RFC 6962 §2.1.2)."""
+    ctx = ctx or default_context()
+    lib = _abi.load()
+    m = len(first_sizes)
+    fs = np.ascontiguousarray(first_sizes, dtype=np.uint64)
+    fr = np.frombuffer(b"".join(first_roots), dtype=np.uint8).copy() if m else np.zeros(32, dtype=np.uint8)
+    off = np.zeros(m + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(p) for p in proofs])
+    flat = np.frombuffer(b"".join(b"".join(p) for p in proofs), dtype=np.uint8).copy() if off[-1] else np.zeros(32, dtype=np.uint8)
+    sr = np.frombuffer(second_root, dtype=np.uint8).copy()
+    ok = np.zeros(m, dtype=np.uint8)
+    _abi.check(lib.afc_merkle_verify_consistency_batch(ctx.handle, _abi.ptr(fs), _abi.ptr(fr), second_size, _abi.ptr(sr), _abi.ptr(flat),
+                                                       _abi.ptr(off), m, _abi.ptr(ok)), ctx.handle)
+    return ok.astype(bool)
+
 
 def verify_inclusion_batch(leaf_hashes, indices, tree_size, proofs, root, ctx=None):
     """Bulk offline audit: ok[i] = path i leads from leaf_hashes[i] at position indices[i] to `root` (RFC 9162 §2.1.3.2)."""

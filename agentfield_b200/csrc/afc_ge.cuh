@@ -123,49 +123,100 @@ AFC_HD int ge_frombytes(ge_p3& h, const uint32_t* enc) {
     return ok_pos | ok_neg;
 }
 
-// Table of multiples of the base point, built on the device at afc_init (k_ed_build_tables), radix 256:
-//   comb[i][j] = (j+1) * 256^i * B     i = 0..31, j = 0..127   affine precomputed form, 4096 x 96 B = 384 KB (L2-resident)
-// Row 0 (the 128 small multiples of B, 12 KB) is what verification stages in shared memory.
+// Table of multiples of the base point, built on the device at afc_init (k_ed_build_tables), radix 2^W (W = AFC_BASE_WINDOW):
+//   base[i][j] = (j+1) * 2^(W i) * B     i = 0..256/W-1, j = 0..2^(W-1)-1     affine precomputed form, 96 B per entry
+//   W = 16 (default): 16 x 32768 entries = 48 MB.  A fixed-base multiplication is 16 mixed additions with signed 16-bit
+//                     digits; every lane reads its own 96-byte entry (L2 / HBM gathers, like the per-issuer tables).
+//   W = 8:            32 x 128 entries = 384 KB, 32 mixed additions (the first build of this library; kept for A/B runs).
+// Row 0 starts with the 128 small multiples of B (12 KB) that the generic Straus kernel stages in shared memory.
+// The per-issuer tables of -A stay radix 256 (COMB_ROWS x COMB_COLS): their build cost is paid per key, not per process.
+#ifndef AFC_BASE_WINDOW
+#define AFC_BASE_WINDOW 16
+#endif
 static constexpr int COMB_ROWS = 32, COMB_COLS = 128;
+static constexpr int BASE_W = AFC_BASE_WINDOW, BASE_ROWS = 256 / BASE_W, BASE_COLS = 1 << (BASE_W - 1);
+static constexpr int BASE_CHUNK = 64;            // entries per thread at build time (one field inversion per chunk)
+static_assert(BASE_W == 8 || BASE_W == 16, "base-point window must be 8 or 16 bits");
+static_assert(BASE_COLS % BASE_CHUNK == 0 && BASE_COLS >= COMB_COLS, "chunking");
 
-// One table entry per thread at init: (j+1) * 256^i * B.
-template <class F = FeInline>
-AFC_HD void ge_build_comb_entry(ge_precomp& out, int i, int j) {
-    ge_p3 P, M;
-    fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); F::mul(P.T, P.X, P.Y);
+AFC_HD void sc_recode_base(uint32_t* t, const uint32_t* s) { if (BASE_W == 16) sc_recode65536(t, s); else sc_recode256(t, s); }
+AFC_HD int sc_digit_base(const uint32_t* t, int i) { return BASE_W == 16 ? sc_digit65536(t, i) : sc_digit256(t, i); }
+
+// out[j] = affine precomputed form of M + j P for j = 0..CH-1, with ONE field inversion (Montgomery's trick); on return
+// M has advanced to M + CH P.  c = P in cached form.  Scratch: 4 CH field elements of thread-local memory.
+template <class F, int CH>
+AFC_HD void ge_affine_run(ge_precomp* out, ge_p3& M, const ge_cached& c) {
+    fe X[CH], Y[CH], Z[CH], Pz[CH];
     ge_p1p1 t;
+    fe d2; fe_const(d2, AFC_D2_32);
 #pragma unroll 1
-    for (int k = 0; k < 8 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
-    // M = (j+1) P by left-to-right double-and-add over the 8 bits of (j+1)
-    ge_cached c;
-    ge_p3_to_cached<F>(c, P);
-    int m = j + 1, started = 0;
+    for (int j = 0; j < CH; j++) {
+        fe_copy(X[j], M.X); fe_copy(Y[j], M.Y); fe_copy(Z[j], M.Z);
+        if (j == 0) fe_copy(Pz[0], M.Z); else F::mul(Pz[j], Pz[j - 1], M.Z);
+        ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
+    }
+    fe inv; fe_invert<F>(inv, Pz[CH - 1]);               // 1 / (Z_0 ... Z_{CH-1})
+#pragma unroll 1
+    for (int j = CH - 1; j >= 0; j--) {
+        fe zi;
+        if (j > 0) { F::mul(zi, inv, Pz[j - 1]); F::mul(inv, inv, Z[j]); } else fe_copy(zi, inv);
+        fe x, y, xy;
+        F::mul(x, X[j], zi); F::mul(y, Y[j], zi);
+        ge_precomp& r = out[j];
+        fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); F::mul(xy, x, y); F::mul(r.xy2d, xy, d2);
+    }
+}
+
+// M = m P for 1 <= m < 2^17, left-to-right double-and-add.  c = P in cached form.
+template <class F = FeInline>
+AFC_HD void ge_small_multiple(ge_p3& M, const ge_p3& P, const ge_cached& c, uint32_t m) {
+    ge_p1p1 t;
+    int started = 0;
     M = P;
 #pragma unroll 1
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = 16; bit >= 0; bit--) {
         if (started) { ge_dbl<F>(t, M.X, M.Y, M.Z); ge_p1p1_to_p3<F>(M, t); }
         if ((m >> bit) & 1) {
             if (started) { ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t); }
             else { M = P; started = 1; }
         }
     }
-    ge_p3_to_precomp<F>(out, M);
 }
 
-// h = a * B for a reduced scalar a (< 2^253): 32 mixed additions (signed radix-256 digits), no doublings.
+// One chunk of the base-point table per thread at init: out[0..BASE_CHUNK) = (j0+1 .. j0+BASE_CHUNK) * 2^(W i) * B.
 template <class F = FeInline>
-AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* comb) {
+AFC_HD void ge_build_base_chunk(ge_precomp* out, int i, int j0) {
+    ge_p3 P, M;
+    fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); F::mul(P.T, P.X, P.Y);
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int k = 0; k < BASE_W * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
+    ge_cached c;
+    ge_p3_to_cached<F>(c, P);
+    ge_small_multiple<F>(M, P, c, (uint32_t)j0 + 1);
+    ge_affine_run<F, BASE_CHUNK>(out, M, c);
+}
+
+// h = a * B for a reduced scalar a (< 2^253): one mixed addition per signed radix-2^W digit, no doublings.
+template <class F = FeInline>
+AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* base) {
     uint32_t t[8];
-    sc_recode256(t, a);
+    sc_recode_base(t, a);
     ge_p3_0(h);
 #pragma unroll 1
-    for (int i = 0; i < 32; i++) {
-        int d = sc_digit256(t, i);
+    for (int i = 0; i < BASE_ROWS; i++) {
+        int d = sc_digit_base(t, i);
+#if AFC_DEVICE_CODE
+        if (BASE_W == 16 && i + 1 < BASE_ROWS) {       // the next entry is a random 96-byte read: start it now
+            int nd = sc_digit_base(t, i + 1), nm = nd < 0 ? -nd : nd;
+            if (nm) { const char* p = (const char*)&base[(size_t)(i + 1) * BASE_COLS + (nm - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+        }
+#endif
         if (d != 0) {
             int neg = d < 0;
             int m = neg ? -d : d;
             ge_p1p1 r;
-            ge_maddsub<F>(r, h, comb[i * COMB_COLS + (m - 1)], neg);
+            ge_maddsub<F>(r, h, base[(size_t)i * BASE_COLS + (m - 1)], neg);
             ge_p1p1_to_p3<F>(h, r);
         }
     }
@@ -181,6 +232,25 @@ AFC_HD void ge_encode_many(uint32_t (*enc)[8], const fe* X, const fe* Y, const f
     for (int g = 1; g < G; g++) F::mul(pz[g], pz[g - 1], Z[g]);
     fe inv; fe_invert<F>(inv, pz[G - 1]);
 #pragma unroll
+    for (int g = G - 1; g >= 0; g--) {
+        fe zi;
+        if (g > 0) { F::mul(zi, inv, pz[g - 1]); F::mul(inv, inv, Z[g]); } else fe_copy(zi, inv);
+        fe x, y;
+        F::mul(x, X[g], zi); F::mul(y, Y[g], zi);
+        fe_towords(enc[g], y);
+        enc[g][7] |= (uint32_t)fe_isnegative(x) << 31;
+    }
+}
+
+// The same with a run-time count G <= GMAX (the table-driven kernels choose G per launch).
+template <class F, int GMAX>
+AFC_HD void ge_encode_group(uint32_t (*enc)[8], const fe* X, const fe* Y, const fe* Z, int G) {
+    fe pz[GMAX];
+    fe_copy(pz[0], Z[0]);
+#pragma unroll 1
+    for (int g = 1; g < G; g++) F::mul(pz[g], pz[g - 1], Z[g]);
+    fe inv; fe_invert<F>(inv, pz[G - 1]);
+#pragma unroll 1
     for (int g = G - 1; g >= 0; g--) {
         fe zi;
         if (g > 0) { F::mul(zi, inv, pz[g - 1]); F::mul(inv, inv, Z[g]); } else fe_copy(zi, inv);
@@ -287,48 +357,33 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
 #define AFC_KEYROW_CHUNK 64      // measured per 1024 keys: 16 -> 2.44 ms, 32 -> 2.19 ms, 64 -> 2.05 ms (8 KB of thread-local scratch)
 #endif
     constexpr int CH = AFC_KEYROW_CHUNK;
-    fe d2; fe_const(d2, AFC_D2_32);
 #pragma unroll 1
-    for (int c0 = 0; c0 < COMB_COLS; c0 += CH) {
-        fe X[CH], Y[CH], Z[CH], Pz[CH];                  // thread-local scratch
-#pragma unroll 1
-        for (int j = 0; j < CH; j++) {
-            fe_copy(X[j], M.X); fe_copy(Y[j], M.Y); fe_copy(Z[j], M.Z);
-            if (j == 0) fe_copy(Pz[0], M.Z); else F::mul(Pz[j], Pz[j - 1], M.Z);
-            ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);
-        }
-        fe inv; fe_invert<F>(inv, Pz[CH - 1]);           // 1 / (Z_0 ... Z_15)
-#pragma unroll 1
-        for (int j = CH - 1; j >= 0; j--) {
-            fe zi;
-            if (j > 0) { F::mul(zi, inv, Pz[j - 1]); F::mul(inv, inv, Z[j]); } else fe_copy(zi, inv);
-            fe x, y, xy;
-            F::mul(x, X[j], zi); F::mul(y, Y[j], zi);
-            ge_precomp& r = row[c0 + j];
-            fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); F::mul(xy, x, y); F::mul(r.xy2d, xy, d2);
-        }
-    }
+    for (int c0 = 0; c0 < COMB_COLS; c0 += CH) ge_affine_run<F, CH>(row + c0, M, c);
     return ok;
 }
 
-// R' = [S]B + [k](-A) through the two radix-256 tables, left in projective form (X : Y : Z).
-// atab: that key's 32 x 128 table of -A; comb: the base-point table.
+// R' = [S]B + [k](-A) through the two tables, left in projective form (X : Y : Z): 32 mixed additions from the key's
+// radix-256 table of -A and 256/W from the base-point table, no doublings.
 template <class F = FeInline>
-AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* comb) {
+AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* base) {
     uint32_t kt[8], st[8];
     sc_recode256(kt, k);
-    sc_recode256(st, sig + 8);
+    sc_recode_base(st, sig + 8);
+    constexpr int SH = BASE_W == 16 ? 1 : 0;            // the base table advances one row every 2^SH rows of the key table
     ge_p3 h; ge_p3_0(h);
     ge_p1p1 t;
 #pragma unroll 1
-    for (int i = 0; i < 32; i++) {
-        int dk = sc_digit256(kt, i), ds = sc_digit256(st, i);
+    for (int i = 0; i < COMB_ROWS; i++) {
+        int dk = sc_digit256(kt, i);
+        int ds = (i & ((1 << SH) - 1)) ? 0 : sc_digit_base(st, i >> SH);
 #if AFC_DEVICE_CODE
-        if (i + 1 < 32) {       // the next row's two entries are random 96-byte reads (HBM / L2): start them now
-            int nk = sc_digit256(kt, i + 1), ns = sc_digit256(st, i + 1);
-            int mk = nk < 0 ? -nk : nk, ms = ns < 0 ? -ns : ns;
+        if (i + 1 < COMB_ROWS) {       // the next rows' entries are random 96-byte reads (HBM / L2): start them now
+            int nk = sc_digit256(kt, i + 1), mk = nk < 0 ? -nk : nk;
             if (mk) { const char* p = (const char*)&atab[(i + 1) * COMB_COLS + (mk - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
-            if (ms) { const char* p = (const char*)&comb[(i + 1) * COMB_COLS + (ms - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+            if (!((i + 1) & ((1 << SH) - 1))) {
+                int ns = sc_digit_base(st, (i + 1) >> SH), ms = ns < 0 ? -ns : ns;
+                if (ms) { const char* p = (const char*)&base[(size_t)((i + 1) >> SH) * BASE_COLS + (ms - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+            }
         }
 #endif
         if (dk != 0) {
@@ -338,7 +393,7 @@ AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const 
         }
         if (ds != 0) {
             int neg = ds < 0, m = neg ? -ds : ds;
-            ge_maddsub<F>(t, h, comb[i * COMB_COLS + (m - 1)], neg);
+            ge_maddsub<F>(t, h, base[(size_t)(i >> SH) * BASE_COLS + (m - 1)], neg);
             ge_p1p1_to_p3<F>(h, t);
         }
     }

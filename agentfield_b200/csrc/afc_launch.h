@@ -51,6 +51,8 @@ cudaError_t merkle_gather_proofs(const uint8_t* const* levels, const uint64_t* s
                                  uint8_t* out, uint32_t* lens, cudaStream_t s, LaunchLog* lg);
 cudaError_t merkle_verify_inclusion(const uint8_t* leaf_hashes, const uint64_t* indices, uint64_t tree_size, const uint8_t* proofs,
                                     const uint32_t* proof_off, const uint8_t* root, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg);
+cudaError_t merkle_verify_consistency(const uint64_t* first_sizes, const uint8_t* first_roots, uint64_t second_size, const uint8_t* second_root,
+                                      const uint8_t* proofs, const uint32_t* proof_off, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg);
 cudaError_t b64url_encode(const uint8_t* in, uint32_t item, uint32_t n, uint8_t* out, cudaStream_t s, LaunchLog* lg);
 cudaError_t hex_encode(const uint8_t* in, uint64_t total, uint8_t* out, cudaStream_t s, LaunchLog* lg);
 cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t threads, uint32_t* sink, cudaStream_t s, LaunchLog* lg);
@@ -73,6 +75,10 @@ struct KeyCache {
     uint32_t bmask;
     uint32_t* rep;          // per-call: n
     uint32_t* kid;          // per-call: n
+    // the cache work of a call (de-duplication, table build) runs on `side`, a high-priority stream, between ev_fork and
+    // ev_join, while the caller's stream computes H(R||A||M), which does not depend on the cache
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
 };
 // scratch_k: n * 32 bytes; kc: nullable (nullptr = always the generic Straus kernel)
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,

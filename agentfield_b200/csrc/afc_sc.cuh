@@ -104,4 +104,12 @@ AFC_HD void sc_recode256(uint32_t* t, const uint32_t* s) {
 }
 AFC_HD int sc_digit256(const uint32_t* t, int i) { return (int)((t[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
 
+// Signed radix-65536 recoding of s < 2^254: t = s + 0x8000..8000; digit_i = half_i(t) - 32768 in [-32768, 32767].
+AFC_HD void sc_recode65536(uint32_t* t, const uint32_t* s) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)s[i] + 0x80008000u; t[i] = (uint32_t)c; c >>= 32; }
+}
+AFC_HD int sc_digit65536(const uint32_t* t, int i) { return (int)((t[i >> 1] >> ((i & 1) * 16)) & 65535u) - 32768; }
+
 }  // namespace afc

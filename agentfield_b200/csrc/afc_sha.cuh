@@ -238,6 +238,8 @@ AFC_HD void store_digest256(uint8_t* out, const uint32_t st[8]) {
 }
 
 // ---------------------------------------------------------------------------------- SHA-512
+// (Moving the 64-bit adds to the FMA pipe the way AFC_FADD does for SHA-256 does not work here: ptxas splits
+// mad.wide.u32 d, a, ONE, c64 into IMAD.WIDE + IADD3 + IMAD.X, so the ALU pipe keeps its add and the FMA pipe gains two.)
 AFC_OUTLINE void sha512_compress(uint64_t* st, uint64_t* w) {
     uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1

@@ -23,8 +23,9 @@ using namespace afc;
 namespace {
 
 constexpr int kLanes = 4;                 // concurrent host-buffer calls per context
-constexpr uint32_t kChunkItems = 1u << 16;  // items per pipeline chunk for host-buffer calls
-constexpr size_t kChunkBytes = 48u << 20;   // and at most this many message bytes per chunk
+constexpr int kSlots = 4;                 // chunks in flight per call: copies keep streaming while an earlier chunk computes
+constexpr uint32_t kChunkItems = 1u << 17;  // items per pipeline chunk for host-buffer calls (one full wave of the table-driven verify at G = 2)
+constexpr size_t kChunkBytes = 96u << 20;   // and at most this many message bytes per chunk
 
 struct DevBuf {
     uint8_t* p = nullptr;
@@ -55,14 +56,14 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// One half of a lane's double buffer
+// One stage of a lane's ring of in-flight chunks
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf msgs, off, a, b, k, out, koff;   // a: pks/seeds/keys  b: sigs
     PinBuf h_in, h_out;                      // bounce buffers when the caller's memory is not pinned
 };
 struct Lane {
-    Slot slot[2];
+    Slot slot[kSlots];
     bool busy = false;
 };
 
@@ -164,6 +165,9 @@ void kc_free(afc_ctx* ctx) {
     launch::KeyCache& k = ctx->kc;
     void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.state, k.build_list, k.bslots, k.rep, k.kid};
     for (void* p : ps) if (p) cudaFree(p);
+    if (k.side) cudaStreamDestroy(k.side);
+    if (k.ev_fork) cudaEventDestroy(k.ev_fork);
+    if (k.ev_join) cudaEventDestroy(k.ev_join);
     k = launch::KeyCache{};
     ctx->kc_ready = false; ctx->kc_call_cap = 0;
 }
@@ -175,11 +179,16 @@ const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
     if (!ctx->kc_ready) {
         uint32_t cap = 1; while (cap < 4 * ctx->kc_max_keys) cap <<= 1;
         k.slot_mask = cap - 1; k.max_keys = ctx->kc_max_keys;
+        int prio_least = 0, prio_greatest = 0;
         bool ok = cudaMalloc((void**)&k.slots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.cpks, (size_t)k.max_keys * 32) == cudaSuccess &&
                   cudaMalloc((void**)&k.valid, k.max_keys) == cudaSuccess && cudaMalloc(&k.tabs, launch::ed_key_table_bytes(k.max_keys)) == cudaSuccess &&
                   cudaMalloc((void**)&k.state, 8 * 4) == cudaSuccess && cudaMalloc((void**)&k.build_list, (size_t)k.max_keys * 4) == cudaSuccess &&
                   cudaMemset(k.slots, 0xff, (size_t)cap * 4) == cudaSuccess && cudaMemset(k.state, 0, 8 * 4) == cudaSuccess &&
                   cudaMemset(k.valid, 0, k.max_keys) == cudaSuccess &&
+                  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&k.side, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&k.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&k.ev_join, cudaEventDisableTiming) == cudaSuccess &&
                   (ctx->kc_event || cudaEventCreateWithFlags(&ctx->kc_event, cudaEventDisableTiming) == cudaSuccess);
         if (!ok) { cudaGetLastError(); kc_free(ctx); ctx->kc_max_keys = 0; return nullptr; }     // no room: stay generic
         ctx->kc_ready = true;
@@ -259,7 +268,7 @@ struct BatchArgs {
     uint8_t* out; size_t out_item;
 };
 
-// Generic chunked pipeline for host-buffer calls: two slots alternate so chunk c+1's H2D overlaps chunk c's kernels.
+// Generic chunked pipeline for host-buffer calls: a ring of kSlots chunks in flight so the H2D of later chunks overlaps the kernels of earlier ones.
 int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     if (A.n == 0) return AFC_OK;
     CK(cudaSetDevice(ctx->device));
@@ -272,7 +281,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     CallLog lc(ctx, 2 * (int)(A.n / kChunkItems + 2) + 8);
     uint32_t i0 = 0;
     int which = 0;
-    struct Pending { uint32_t i0, cnt; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    struct Pending { uint32_t i0, cnt; bool active; } pend[kSlots] = {};
     auto drain = [&](int w) -> int {
         if (!pend[w].active) return AFC_OK;
         Slot& sl = lane.slot[w];
@@ -354,11 +363,13 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         CK(cudaMemcpyAsync(pin_out ? A.out + (size_t)i0 * A.out_item : sl.h_out.p, sl.out.p, (size_t)cnt * A.out_item,
                            cudaMemcpyDeviceToHost, sl.stream));
         pend[which] = {i0, cnt, true};
-        which ^= 1;
+        which = (which + 1) % kSlots;
         i0 = i1;
     }
-    int rc = drain(0); if (rc != AFC_OK) return rc;
-    rc = drain(1); if (rc != AFC_OK) return rc;
+    for (int w = 0; w < kSlots; w++) {      // oldest first
+        int rc = drain((which + w) % kSlots);
+        if (rc != AFC_OK) return rc;
+    }
     return AFC_OK;
 }
 
@@ -401,7 +412,7 @@ int afc_init(int device, afc_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
     if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     for (int l = 0; l < kLanes; l++)
-        for (int s = 0; s < 2; s++)
+        for (int s = 0; s < kSlots; s++)
             if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&ctx->comb, launch::ed_tables_bytes())) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
     CallLog lc(ctx);
@@ -417,7 +428,7 @@ void afc_destroy(afc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     afc_comm_destroy(ctx);
     for (int l = 0; l < kLanes; l++)
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < kSlots; s++) {
             Slot& sl = ctx->lanes[l].slot[s];
             if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
             sl.msgs.release(); sl.off.release(); sl.a.release(); sl.b.release(); sl.k.release(); sl.out.release(); sl.koff.release();
@@ -970,6 +981,64 @@ int afc_merkle_verify_inclusion_batch(afc_ctx* ctx, const uint8_t* leaf_hashes32
     }
     if (e == cudaSuccess) e = cudaMemcpy(ok, d_ok, m, cudaMemcpyDeviceToHost);
     cudaFree(d_lh); cudaFree(d_pr); cudaFree(d_root); cudaFree(d_ok); cudaFree(d_idx); cudaFree(d_po);
+    CK(e);
+    return AFC_OK;
+}
+
+// RFC 6962 §2.1.2 PROOF(first, D[n]) read out of the materialised levels.  Every node of the proof is MTH(D[a:b]) with a
+// a multiple of 2^l and b = min(a + 2^l, n): exactly node (level l, index a >> l) of the tree (a lone right node is promoted
+// unchanged, which is what the RFC's largest-power-of-two split yields for a ragged right edge).
+namespace {
+void consistency_nodes(uint64_t m, uint64_t lo, uint64_t hi, bool whole, std::vector<std::pair<int, uint64_t>>& out) {
+    const uint64_t n = hi - lo;
+    auto node = [&](uint64_t a, uint64_t width_pow2) { int l = 0; while ((1ull << l) < width_pow2) l++; out.emplace_back(l, a >> l); };
+    auto pow2_ceil = [](uint64_t w) { uint64_t p = 1; while (p < w) p <<= 1; return p; };
+    if (m == n) { if (!whole) node(lo, pow2_ceil(n)); return; }
+    uint64_t k = 1; while (k * 2 < n) k *= 2;
+    if (m <= k) { consistency_nodes(m, lo, lo + k, whole, out); node(lo + k, k); }
+    else { consistency_nodes(m - k, lo + k, hi, false, out); node(lo, k); }
+}
+}  // namespace
+int afc_merkle_tree_consistency_proof(afc_merkle_tree* t, uint64_t first, uint8_t* proof, uint32_t* n_nodes) {
+    if (!t || !n_nodes || first == 0 || first > t->n) return AFC_EINVAL;
+    afc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<std::pair<int, uint64_t>> nodes;
+    consistency_nodes(first, 0, t->n, true, nodes);
+    if (nodes.size() && !proof) return AFC_EINVAL;
+    for (size_t i = 0; i < nodes.size(); i++) {
+        const int l = nodes[i].first; const uint64_t j = nodes[i].second;
+        if (l >= (int)t->levels.size() || j >= t->sizes[l]) return AFC_ESTATE;
+        CK(cudaMemcpy(proof + 32 * i, t->levels[l] + 32 * j, 32, cudaMemcpyDeviceToHost));
+    }
+    *n_nodes = (uint32_t)nodes.size();
+    return AFC_OK;
+}
+int afc_merkle_verify_consistency_batch(afc_ctx* ctx, const uint64_t* first_sizes, const uint8_t* first_roots32, uint64_t second_size,
+                                        const uint8_t second_root32[32], const uint8_t* proofs, const uint32_t* proof_off, uint32_t m, uint8_t* ok) {
+    if (!ctx || (m && (!first_sizes || !first_roots32 || !second_root32 || !proof_off || !ok))) return AFC_EINVAL;
+    if (m == 0) return AFC_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t pn = proof_off[m];
+    if (pn && !proofs) return AFC_EINVAL;
+    uint8_t *d_fr = nullptr, *d_pr = nullptr, *d_sr = nullptr, *d_ok = nullptr; uint64_t* d_fs = nullptr; uint32_t* d_po = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_fr, (size_t)m * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_pr, (pn ? pn : 1) * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_sr, 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_ok, m);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_fs, (size_t)m * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_po, (size_t)(m + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_fr, first_roots32, (size_t)m * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && pn) e = cudaMemcpy(d_pr, proofs, pn * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_sr, second_root32, 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_fs, first_sizes, (size_t)m * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_po, proof_off, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        CallLog lc(ctx);
+        e = launch::merkle_verify_consistency(d_fs, d_fr, second_size, d_sr, d_pr, d_po, m, d_ok, 0, lc);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(ok, d_ok, m, cudaMemcpyDeviceToHost);
+    cudaFree(d_fr); cudaFree(d_pr); cudaFree(d_sr); cudaFree(d_ok); cudaFree(d_fs); cudaFree(d_po);
     CK(e);
     return AFC_OK;
 }

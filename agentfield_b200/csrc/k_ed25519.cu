@@ -30,9 +30,12 @@ __device__ __forceinline__ void store_words8(uint8_t* p, const uint32_t* w) {
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-__global__ void k_ed_build_tables(ge_precomp* comb) {
+// one thread per BASE_CHUNK consecutive entries of one row of the base-point table (afc_init, once per context)
+__global__ void __launch_bounds__(32)
+k_ed_build_tables(ge_precomp* base) {
+    constexpr int CPR = BASE_COLS / BASE_CHUNK;      // chunks per row
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < COMB_ROWS * COMB_COLS) ge_build_comb_entry<FeCall>(comb[t], t / COMB_COLS, t % COMB_COLS);
+    if (t < BASE_ROWS * CPR) ge_build_base_chunk<FeCall>(base + (size_t)t * BASE_CHUNK, t / CPR, (t % CPR) * BASE_CHUNK);
 }
 
 __global__ void __launch_bounds__(ED_THREADS)
@@ -75,10 +78,50 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
 }
 
 // ---- keyed verification (identity cache): per-key radix-256 tables of -A, built once per key set
-#ifndef AFC_KC_GROUP
-#define AFC_KC_GROUP 4
-#endif
-constexpr int KC_GROUP = AFC_KC_GROUP;   // credentials per thread in the table-driven kernels (one shared field inversion)
+// Credentials per thread in the table-driven kernels (they share ONE field inversion, Montgomery's trick).  The group size is a
+// launch parameter: every thread does the same work, so a launch runs in whole waves of `resident threads`; pick_group() chooses
+// G in [1, KC_GMAX] so that the last wave is full (1 M credentials on 148 SMs x 512 threads: G = 4 is 3.3 waves = 82 % busy,
+// G = 7 is 1.9 waves = 94 % busy with a smaller inversion share).
+constexpr int KC_GMAX = 8;
+
+// Shared body: thread t of T handles credentials t, t + T, t + 2T, ... (G of them; lanes stay adjacent in memory).
+// lookup(i, atab) -> false when credential i's key is unknown or does not decode (ok = 0, arithmetic skipped).
+template <class Lookup>
+__device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
+                                                   const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
+    uint32_t good = 0;
+#pragma unroll 1
+    for (int g = 0; g < G; g++) {
+        uint64_t i = (uint64_t)t + (uint64_t)g * T;
+        fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
+        if (i >= n) continue;
+        const ge_precomp* atab;
+        if (!lookup((uint32_t)i, atab)) continue;
+        uint32_t sig[16], k[8];
+        load_words8(sig, sigs + 64ull * i);
+        load_words8(sig + 8, sigs + 64ull * i + 32);
+        load_words8(k, (const uint8_t*)(ks + 8ull * i));
+        if (!ed25519_sig_wellformed(sig)) continue;
+        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, atab, base);
+        good |= 1u << g;
+    }
+    uint32_t enc[KC_GMAX][8];
+    ge_encode_group<FeInline, KC_GMAX>(enc, X, Y, Z, G);
+#pragma unroll 1
+    for (int g = 0; g < G; g++) {
+        uint64_t i = (uint64_t)t + (uint64_t)g * T;
+        if (i >= n) break;
+        uint32_t r[8];
+        load_words8(r, sigs + 64ull * i);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
+        ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
+    }
+}
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_key_rows(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_precomp* __restrict__ tabs, uint8_t* __restrict__ valid) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,39 +152,13 @@ k_ed_hram_keyed(const uint8_t* __restrict__ key_pks, const uint32_t* __restrict_
 __global__ void __launch_bounds__(ED_THREADS, 3)
 k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                   const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
-                  const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((uint64_t)t * KC_GROUP >= n) return;
-    fe X[KC_GROUP], Y[KC_GROUP], Z[KC_GROUP];
-    uint32_t good = 0;
-#pragma unroll 1
-    for (int g = 0; g < KC_GROUP; g++) {
-        uint32_t i = t * KC_GROUP + g;
-        fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
-        if (i >= n) continue;
+                  const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
+    table_verify_group([&](uint32_t i, const ge_precomp*& atab) {
         uint32_t key = key_index[i];
-        if (key >= n_keys || !valid[key]) continue;          // unknown index or undecodable key: ok = 0
-        uint32_t sig[16], k[8];
-        load_words8(sig, sigs + 64ull * i);
-        load_words8(sig + 8, sigs + 64ull * i + 32);
-        load_words8(k, (const uint8_t*)(ks + 8ull * i));
-        if (!ed25519_sig_wellformed(sig)) continue;
-        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, tabs + (size_t)key * COMB_ROWS * COMB_COLS, comb);
-        good |= 1u << g;
-    }
-    uint32_t enc[KC_GROUP][8];
-    ge_encode_many<FeInline, KC_GROUP>(enc, X, Y, Z);
-#pragma unroll 1
-    for (int g = 0; g < KC_GROUP; g++) {
-        uint32_t i = t * KC_GROUP + g;
-        if (i >= n) break;
-        uint32_t r[8];
-        load_words8(r, sigs + 64ull * i);
-        uint32_t diff = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
-        ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
-    }
+        if (key >= n_keys || !valid[key]) return false;      // unknown index or undecodable key: ok = 0
+        atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
+        return true;
+    }, comb, sigs, ks, n, T, G, ok);
 }
 
 // ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
@@ -253,43 +270,16 @@ k_kc_build(KeyCacheDev kc) {
 }
 // (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
 // the register allocation of the curve loop around and nothing overlaps that did not already.)
-// Each thread handles KC_GROUP consecutive credentials and shares ONE field inversion between their final encodings
-// (Montgomery's trick): the inversion is a quarter of this kernel's multiplier work when done per credential.
 __global__ void __launch_bounds__(ED_THREADS, 3)
 k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
-                   uint32_t n, uint8_t* __restrict__ ok) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((uint64_t)t * KC_GROUP >= n || !kc.state[1]) return;
-    fe X[KC_GROUP], Y[KC_GROUP], Z[KC_GROUP];
-    uint32_t good = 0;
-#pragma unroll 1
-    for (int g = 0; g < KC_GROUP; g++) {
-        uint32_t i = t * KC_GROUP + g;
-        fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
-        if (i >= n) continue;
+                   uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
+    if (!kc.state[1]) return;
+    table_verify_group([&](uint32_t i, const ge_precomp*& atab) {
         uint32_t id = kc.kid[kc.rep[i]];
-        if (!kc.valid[id]) continue;                         // key does not decode: ok = 0, arithmetic skipped
-        uint32_t sig[16], k[8];
-        load_words8(sig, sigs + 64ull * i);
-        load_words8(sig + 8, sigs + 64ull * i + 32);
-        load_words8(k, (const uint8_t*)(ks + 8ull * i));
-        if (!ed25519_sig_wellformed(sig)) continue;
-        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS, comb);
-        good |= 1u << g;
-    }
-    uint32_t enc[KC_GROUP][8];
-    ge_encode_many<FeInline, KC_GROUP>(enc, X, Y, Z);
-#pragma unroll 1
-    for (int g = 0; g < KC_GROUP; g++) {
-        uint32_t i = t * KC_GROUP + g;
-        if (i >= n) break;
-        uint32_t r[8];
-        load_words8(r, sigs + 64ull * i);
-        uint32_t diff = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
-        ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
-    }
+        if (!kc.valid[id]) return false;                     // key does not decode: ok = 0
+        atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
+        return true;
+    }, comb, sigs, ks, n, T, G, ok);
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index
@@ -478,10 +468,36 @@ namespace launch {
 
 static inline uint32_t blocks_for(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
 
-size_t ed_tables_bytes() { return sizeof(ge_precomp) * COMB_ROWS * COMB_COLS; }
+// Group size for a table-driven launch of n credentials: minimise waves(G) x (G x main + inversion), in field multiplications.
+static int pick_group(uint32_t n, const void* kernel) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("AFC_KC_GROUP"); forced = e ? atoi(e) : 0; }
+    if (forced >= 1 && forced <= KC_GMAX) return forced;
+    static thread_local int resident[2] = {0, 0};
+    static thread_local const void* which[2] = {nullptr, nullptr};
+    int slot = (which[0] == kernel || which[0] == nullptr) ? 0 : 1;
+    if (which[slot] != kernel || !resident[slot]) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ED_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 3; }
+        which[slot] = kernel; resident[slot] = sms * per_sm * ED_THREADS;
+    }
+    const uint64_t R = (uint64_t)resident[slot];
+    const uint64_t c_main = (uint64_t)(COMB_ROWS + BASE_ROWS) * 7 + 12, c_inv = 270;
+    int best = 1; uint64_t best_cost = ~0ull;
+    for (int G = 1; G <= KC_GMAX; G++) {
+        uint64_t T = ((uint64_t)n + G - 1) / G, waves = (T + R - 1) / R;
+        uint64_t cost = waves * (G * c_main + c_inv);
+        if (cost < best_cost) { best_cost = cost; best = G; }
+    }
+    return best;
+}
+
+size_t ed_tables_bytes() { return sizeof(ge_precomp) * (size_t)BASE_ROWS * BASE_COLS; }
 
 cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
-    AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<COMB_ROWS * COMB_COLS / 64, 64, 0, s>>>((ge_precomp*)comb));
+    AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<blocks_for((uint64_t)BASE_ROWS * BASE_COLS / BASE_CHUNK, 32), 32, 0, s>>>((ge_precomp*)comb));
     return cudaGetLastError();
 }
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
@@ -490,24 +506,36 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
     const ge_precomp* cb = (const ge_precomp*)comb;
     const uint32_t nb = blocks_for(n, ED_THREADS);
     const uint32_t* skip = nullptr;
-    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+    if (!kcp) AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
     if (kcp) {
-        // issuer-key cache: de-duplicate, look up, decide on the device, build what is missing, verify through tables
+        // Issuer-key cache: de-duplicate, look up, decide on the device, build what is missing, verify through tables.
+        // The cache work runs on kc.side (a HIGH-priority stream: its small CTAs are dispatched as soon as SM slots free up)
+        // while H(R||A||M), which does not depend on the cache, runs on the caller's stream: the table build (IMAD.WIDE-bound,
+        // 1 warp per CTA, low occupancy) and the hashing (ALU-bound) share the SMs.  With equal priorities the block
+        // dispatcher drains the hashing grid first and nothing overlaps (measured).
         const KeyCache kc = *kcp;
-        cudaError_t e = cudaMemsetAsync(kc.bslots, 0xff, ((size_t)kc.bmask + 1) * 4, s);
+        const cudaStream_t q = kc.side;
+        cudaError_t e = cudaEventRecord(kc.ev_fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(q, kc.ev_fork, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(kc.bslots, 0xff, ((size_t)kc.bmask + 1) * 4, q);
         if (e != cudaSuccess) return e;
-        AFC_LAUNCH(lg, "k_kc_begin", s, k_kc_begin<<<1, 32, 0, s>>>(kc));
-        AFC_LAUNCH(lg, "k_kc_dedup", s, k_kc_dedup<<<blocks_for(n, 256), 256, 0, s>>>(kc, pks, n));
-        AFC_LAUNCH(lg, "k_kc_mode", s, k_kc_mode<<<1, 32, 0, s>>>(kc, n));
-        AFC_LAUNCH(lg, "k_kc_reset", s, k_kc_reset<<<64, 256, 0, s>>>(kc));
-        AFC_LAUNCH(lg, "k_kc_insert", s, k_kc_insert<<<blocks_for(n, 256), 256, 0, s>>>(kc, pks, n));
+        AFC_LAUNCH(lg, "k_kc_begin", q, k_kc_begin<<<1, 32, 0, q>>>(kc));
+        AFC_LAUNCH(lg, "k_kc_dedup", q, k_kc_dedup<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
+        AFC_LAUNCH(lg, "k_kc_mode", q, k_kc_mode<<<1, 32, 0, q>>>(kc, n));
+        AFC_LAUNCH(lg, "k_kc_reset", q, k_kc_reset<<<64, 256, 0, q>>>(kc));
+        AFC_LAUNCH(lg, "k_kc_insert", q, k_kc_insert<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
         // at most min(max_keys, n / KC_AMORTISE) tables can be due in one call
         uint64_t max_build = kc.max_keys < n / KC_AMORTISE ? kc.max_keys : n / KC_AMORTISE;
         if (max_build)
             // one warp per CTA: 32 x keys small CTAs spread evenly over the 148 SMs (128-thread CTAs left half of them with
             // twice the work of the rest: 2.44 ms vs the arithmetic floor of ~1.4 ms for 1024 keys)
-            AFC_LAUNCH(lg, "k_kc_build", s, k_kc_build<<<blocks_for(max_build * COMB_ROWS, 32), 32, 0, s>>>(kc));
-        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(((uint64_t)n + KC_GROUP - 1) / KC_GROUP, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, ok));
+            AFC_LAUNCH(lg, "k_kc_build", q, k_kc_build<<<blocks_for(max_build * COMB_ROWS, 32), 32, 0, q>>>(kc));
+        if ((e = cudaEventRecord(kc.ev_join, q)) != cudaSuccess) return e;
+        AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+        if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
+        const int G = pick_group(n, (const void*)k_ed_verify_cached);
+        const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
+        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, T, G, ok));
         skip = kc.state + 1;
     }
     static int variant = -1;
@@ -529,7 +557,9 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
                                   uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
-    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(((uint64_t)n + KC_GROUP - 1) / KC_GROUP, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok));
+    const int G = pick_group(n, (const void*)k_ed_verify_keyed);
+    const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
+    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, T, G, ok));
     return cudaGetLastError();
 }
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,

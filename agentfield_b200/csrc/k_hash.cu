@@ -190,6 +190,58 @@ k_merkle_verify_inclusion(const uint8_t* __restrict__ leaf_hashes, const uint64_
     ok[t] = (uint8_t)(good && sn == 0 && diff == 0);
 }
 
+// RFC 9162 §2.1.4.2 consistency verification, one proof per thread: the tree of second_size leaves with root second_root
+// extends the tree of first_sizes[t] leaves with root first_roots[t].  Proofs packed as for inclusion.
+__global__ void __launch_bounds__(HASH_THREADS)
+k_merkle_verify_consistency(const uint64_t* __restrict__ first_sizes, const uint8_t* __restrict__ first_roots, uint64_t second_size,
+                            const uint8_t* __restrict__ second_root, const uint8_t* __restrict__ proofs,
+                            const uint32_t* __restrict__ proof_off, uint32_t m, uint8_t* __restrict__ ok) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const uint64_t first = first_sizes[t];
+    uint32_t k = proof_off[t];
+    const uint32_t k1 = proof_off[t + 1];
+    uint32_t good = first > 0 && first <= second_size;
+    uint32_t fw[8], sw[8], fr[8], sr[8];
+    load_node(fw, first_roots + 32ull * t);
+    load_node(sw, second_root);
+    uint32_t same = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) same |= fw[i] ^ sw[i];
+    if (!good || first == second_size) { ok[t] = (uint8_t)(good && k == k1 && same == 0); return; }
+    if ((first & (first - 1)) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) fr[i] = fw[i];               // a power of two: the old root itself starts the path
+    } else if (k < k1) {
+        load_node(fr, proofs + 32ull * k); k++;
+    } else { ok[t] = 0; return; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sr[i] = fr[i];
+    uint64_t fn = first - 1, sn = second_size - 1;
+    while (fn & 1) { fn >>= 1; sn >>= 1; }
+    for (; k < k1; k++) {
+        if (sn == 0) { good = 0; break; }
+        uint32_t c[8], o[8];
+        load_node(c, proofs + 32ull * k);
+        if ((fn & 1) || fn == sn) {
+            sha256_merkle_node(o, c, fr);
+#pragma unroll
+            for (int i = 0; i < 8; i++) fr[i] = o[i];
+            sha256_merkle_node(o, c, sr);
+            while (fn && !(fn & 1)) { fn >>= 1; sn >>= 1; }
+        } else {
+            sha256_merkle_node(o, sr, c);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) sr[i] = o[i];
+        fn >>= 1; sn >>= 1;
+    }
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) diff |= (fr[i] ^ fw[i]) | (sr[i] ^ sw[i]);
+    ok[t] = (uint8_t)(good && sn == 0 && diff == 0);
+}
+
 // ---- text codecs either side of the kernels: base64url without padding for signatures / digests
 // (base64.RawURLEncoding in vc_service.go:465,514) and lowercase hex for the webhook header (hex.EncodeToString,
 // webhook_dispatcher.go:473).  Fixed-size records; one thread per 3-byte group / per byte pair.
@@ -292,6 +344,12 @@ cudaError_t merkle_verify_inclusion(const uint8_t* leaf_hashes, const uint64_t* 
                                     const uint32_t* proof_off, const uint8_t* root, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg) {
     if (m == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_merkle_verify_inclusion", s, k_merkle_verify_inclusion<<<blocks_for(m, HASH_THREADS), HASH_THREADS, 0, s>>>(leaf_hashes, indices, tree_size, proofs, proof_off, root, m, ok));
+    return cudaGetLastError();
+}
+cudaError_t merkle_verify_consistency(const uint64_t* first_sizes, const uint8_t* first_roots, uint64_t second_size, const uint8_t* second_root,
+                                      const uint8_t* proofs, const uint32_t* proof_off, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg) {
+    if (m == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_merkle_verify_consistency", s, k_merkle_verify_consistency<<<blocks_for(m, HASH_THREADS), HASH_THREADS, 0, s>>>(first_sizes, first_roots, second_size, second_root, proofs, proof_off, m, ok));
     return cudaGetLastError();
 }
 cudaError_t b64url_encode(const uint8_t* in, uint32_t item, uint32_t n, uint8_t* out, cudaStream_t s, LaunchLog* lg) {

@@ -75,6 +75,17 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        # NVML in a thread (no process start-up latency, so short timed regions still get samples); nvidia-smi -lms as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv, self.stop_flag = pynvml, False
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -82,11 +93,31 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _nvml_loop(self):
+        nv = self.nv
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append("%d, %d, 0, %s" % (sm, mx, ", ".join("Active" if (r & b) else "Not Active" for _, b in bits)))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nv", None):
+            self.stop_flag = True
+            self.th.join(timeout=2)
         if self.proc:
             self.proc.terminate()
             try:
@@ -308,6 +339,19 @@ def main():
     e2e_value = world * n * args.steps / float(t_e.item())
     h2d = n * (32 + 64 + MSG_LEN) + (n + 1) * 8
     d2h = n
+    # the transfer floor of that call: the same pinned buffers copied to the device with nothing else going on
+    scratch = [torch.empty_like(t, device=dev) for t in (h_pks, h_sigs, h_msgs, h_off)]
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(3):
+        if rep == 1:
+            c0.record()
+        for dst, src in zip(scratch, (h_pks, h_sigs, h_msgs, h_off)):
+            dst.copy_(src, non_blocking=True)
+    c1.record(); torch.cuda.synchronize()
+    h2d_only_ms = c0.elapsed_time(c1) / 2
+    del scratch
+    e2e_extra = {"ms_per_step": 1e3 * float(t_e.item()) / args.steps, "h2d_only_ms": h2d_only_ms, "pcie_h2d_GBps": h2d / h2d_only_ms / 1e6,
+                 "note": "h2d_only_ms = the step's inputs copied from the same pinned buffers with no compute: the transfer floor of the host call"}
 
     # ---------------- roofline of the dominant kernel
     hbm_peak, peak_src = peaks()
@@ -334,7 +378,7 @@ def main():
         "config": {"workload": "batched Ed25519 verify, 1 M x 512 B credentials per GPU (BASELINE.json configs[1])", "items_per_gpu": n,
                    "msg_len": MSG_LEN, "keys": N_KEYS, "corrupted": "1%", "l2": "inputs (609 MB per step) larger than L2 (126 MB)",
                    "parallelism": "independent shards, no collective" if world > 1 else "single GPU", "sm_count": info["sm_count"]},
-        "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "clocks": clocks, "e2e": dict({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}, **e2e_extra),
         "gpu_launches": int(launches), "roofline": roofline, "impl": "b200",
     }
 

@@ -174,6 +174,13 @@ int afc_merkle_tree_inclusion_proofs(afc_merkle_tree* t, const uint64_t* indices
                                      uint32_t* proof_lens /* m, in nodes */);
 int afc_merkle_verify_inclusion_batch(afc_ctx* ctx, const uint8_t* leaf_hashes32, const uint64_t* indices, uint64_t tree_size,
                                       const uint8_t* proofs, const uint32_t* proof_off, const uint8_t root32[32], uint32_t m, uint8_t* ok);
+/* RFC 6962 §2.1.2 consistency proof between the first `first` leaves (0 < first <= n) and the whole tree: at most
+ * 2 * max_proof_nodes nodes are written to `proof`, their number to *n_nodes.  afc_merkle_verify_consistency_batch checks
+ * m earlier checkpoints (first_sizes[i], first_roots32[i]) against one later (second_size, second_root32) on the device
+ * (RFC 9162 §2.1.4.2); ok[i] = 0 for first_sizes[i] == 0 or > second_size. */
+int afc_merkle_tree_consistency_proof(afc_merkle_tree* t, uint64_t first, uint8_t* proof, uint32_t* n_nodes);
+int afc_merkle_verify_consistency_batch(afc_ctx* ctx, const uint64_t* first_sizes, const uint8_t* first_roots32, uint64_t second_size,
+                                        const uint8_t second_root32[32], const uint8_t* proofs, const uint32_t* proof_off, uint32_t m, uint8_t* ok);
 
 /* ---- multi-GPU: independent shards, one exchange step --------------------------------
  * Each rank appends its contiguous, 2^k-aligned leaf range to its own afc_merkle; the 32-byte subtree

@@ -117,3 +117,59 @@ def verify_inclusion(leaf_h, m, n, proof, root_h):
         fn >>= 1
         sn >>= 1
     return sn == 0 and r == root_h
+
+
+def consistency_proof(hs, m):
+    """RFC 6962 §2.1.2: PROOF(m, D[n]) over leaf hashes hs (n = len(hs)), 0 < m <= n, by the recursive definition."""
+    n = len(hs)
+    if not 0 < m <= n:
+        raise ValueError("need 0 < m <= n")
+
+    def mth(lo, hi):
+        return root_from_leaf_hashes(hs[lo:hi])
+
+    def sub(m, lo, hi, b):
+        n = hi - lo
+        if m == n:
+            return [] if b else [mth(lo, hi)]
+        k = 1
+        while k * 2 < n:
+            k *= 2
+        if m <= k:
+            return sub(m, lo, lo + k, b) + [mth(lo + k, hi)]
+        return sub(m - k, lo + k, hi, False) + [mth(lo, lo + k)]
+
+    return sub(m, 0, n, True)
+
+
+def verify_consistency(first, second, first_root, second_root, proof):
+    """RFC 9162 §2.1.4.2: the tree of `second` leaves with root second_root extends the tree of `first` leaves with
+    root first_root (iterative algorithm — independent of the recursive construction above)."""
+    if not 0 < first <= second:
+        return False
+    if first == second:
+        return not proof and first_root == second_root
+    path = list(proof)
+    if first & (first - 1) == 0:
+        path = [first_root] + path
+    if not path:
+        return False
+    fn, sn = first - 1, second - 1
+    while fn & 1:
+        fn >>= 1
+        sn >>= 1
+    fr = sr = path[0]
+    for c in path[1:]:
+        if sn == 0:
+            return False
+        if (fn & 1) or fn == sn:
+            fr = node_hash(c, fr)
+            sr = node_hash(c, sr)
+            while fn and not (fn & 1):
+                fn >>= 1
+                sn >>= 1
+        else:
+            sr = node_hash(sr, c)
+        fn >>= 1
+        sn >>= 1
+    return sn == 0 and fr == first_root and sr == second_root

@@ -178,7 +178,24 @@ def make_rfc6962():
     lb = [bytes.fromhex(x) for x in leaves]
     for n in range(1, 9):
         assert M.root(lb[:n]).hex() == roots[n - 1] == M.root_recursive(lb[:n]).hex(), n
-    out = {"leaves": leaves, "roots": roots, "empty_root": hashlib.sha256(b"").hexdigest(), "synthetic": []}
+    # consistency proofs of the same reference tree (certificate-transparency merkle_tree_test.cc): (first, second, nodes)
+    consistency = [
+        {"first": 1, "second": 1, "proof": []},
+        {"first": 1, "second": 8, "proof": ["96a296d224f285c67bee93c30f8a309157f0daa35dc5b87e410b78630a09cfc7",
+                                            "5f083f0a1a33ca076a95279832580db3e0ef4584bdff1f54c8a360f50de3031e",
+                                            "6b47aaf29ee3c2af9af889bc1fb9254dabd31177f16232dd6aab035ca39bf6e4"]},
+        {"first": 6, "second": 8, "proof": ["0ebc5d3437fbe2db158b9f126a1d118e308181031d0a949f8dededebc558ef6a",
+                                            "ca854ea128ed050b41b35ffc1b87b8eb2bde461e9e3b5596ece6b9d5975a0ae0",
+                                            "d37ee418976dd95753c1c73862b9398fa2a2cf9b4ff0fdfe8b30cd95209614b7"]},
+        {"first": 2, "second": 5, "proof": ["5f083f0a1a33ca076a95279832580db3e0ef4584bdff1f54c8a360f50de3031e",
+                                            "bc1a0643b12e4d2d7c77918f44e0f4f79a838b6cf9ec5b5c283e1f4d88599e6b"]},
+    ]
+    hs = [M.leaf_hash(x) for x in lb]
+    for c in consistency:
+        assert [x.hex() for x in M.consistency_proof(hs[:c["second"]], c["first"])] == c["proof"], c
+        assert M.verify_consistency(c["first"], c["second"], bytes.fromhex(roots[c["first"] - 1]), bytes.fromhex(roots[c["second"] - 1]),
+                                    [bytes.fromhex(x) for x in c["proof"]])
+    out = {"leaves": leaves, "roots": roots, "consistency": consistency, "empty_root": hashlib.sha256(b"").hexdigest(), "synthetic": []}
     rng = np.random.default_rng(0xAF6962)
     for n, ln in ((1, 96), (2, 96), (3, 5), (7, 96), (33, 96), (100, 17), (1000, 96), (1025, 96)):
         ls = [rng.integers(0, 256, ln, dtype=np.uint8).tobytes() for _ in range(n)]

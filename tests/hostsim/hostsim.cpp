@@ -16,14 +16,56 @@ using namespace afc;
 static std::vector<ge_precomp> g_comb;
 static void ensure_tables() {
     if (!g_comb.empty()) return;
-    g_comb.resize(COMB_ROWS * COMB_COLS);
-    for (int i = 0; i < COMB_ROWS; i++)
-        for (int j = 0; j < COMB_COLS; j++) ge_build_comb_entry(g_comb[i * COMB_COLS + j], i, j);
+    // the base-point table row by row: one running point per row instead of the device's one-thread-per-chunk start
+    // (ge_build_base_chunk, spot-checked against this table by hs_base_chunk_mismatches)
+    g_comb.resize((size_t)BASE_ROWS * BASE_COLS);
+    ge_p3 P;
+    fe_const(P.X, AFC_BX_32); fe_const(P.Y, AFC_BY_32); fe_1(P.Z); fe_mul(P.T, P.X, P.Y);
+    for (int i = 0; i < BASE_ROWS; i++) {
+        ge_cached c; ge_p3_to_cached(c, P);
+        ge_p3 M = P;
+        for (int j0 = 0; j0 < BASE_COLS; j0 += BASE_CHUNK) ge_affine_run<FeInline, BASE_CHUNK>(&g_comb[(size_t)i * BASE_COLS + j0], M, c);
+        ge_p1p1 t;
+        for (int k = 0; k < BASE_W; k++) { ge_dbl(t, P.X, P.Y, P.Z); ge_p1p1_to_p3(P, t); }
+    }
 }
 static void words_from_bytes(uint32_t* w, const uint8_t* b, int n) { for (int i = 0; i < n; i++) w[i] = load_le32(b + 4 * i); }
 static void bytes_from_words(uint8_t* b, const uint32_t* w, int n) { for (int i = 0; i < n; i++) store_le32(b + 4 * i, w[i]); }
 
 extern "C" {
+
+// number of 32-bit words in which ge_build_base_chunk(i, j0) (what each device thread computes at afc_init) differs from the table
+int hs_base_chunk_mismatches(int i, int j0) {
+    ensure_tables();
+    ge_precomp out[BASE_CHUNK];
+    ge_build_base_chunk(out, i, j0);
+    int bad = 0;
+    for (int j = 0; j < BASE_CHUNK; j++) {
+        const ge_precomp& r = g_comb[(size_t)i * BASE_COLS + j0 + j];
+        uint32_t a[8], b[8];
+        const fe* x[3] = {&out[j].ypx, &out[j].ymx, &out[j].xy2d};
+        const fe* y[3] = {&r.ypx, &r.ymx, &r.xy2d};
+        for (int q = 0; q < 3; q++) { fe_towords(a, *x[q]); fe_towords(b, *y[q]); for (int w = 0; w < 8; w++) bad += a[w] != b[w]; }
+    }
+    return bad;
+}
+int hs_base_window(void) { return BASE_W; }
+// ge_encode_group (one inversion for G points, run-time G) against ge_encode point by point; returns mismatching words
+int hs_encode_group_mismatches(int G, uint32_t seed) {
+    ensure_tables();
+    fe X[8], Y[8], Z[8];
+    uint32_t enc[8][8], one[8];
+    int bad = 0;
+    for (int g = 0; g < G; g++) {
+        uint32_t a[8] = {seed * 2654435761u + g, seed ^ 0x9e3779b9u, (uint32_t)g * 77u + 1u, seed + 3u * g, 5, 6, 7, 0x0fffffffu};
+        ge_p3 h; ge_scalarmult_base(h, a, &g_comb[0]);
+        // make the Z coordinates differ: scale (X:Y:Z) by a point-dependent factor
+        fe f; fe_copy(f, h.Y); fe_mul(X[g], h.X, f); fe_mul(Y[g], h.Y, f); fe_mul(Z[g], h.Z, f);
+    }
+    ge_encode_group<FeInline, 8>(enc, X, Y, Z, G);
+    for (int g = 0; g < G; g++) { ge_encode(one, X[g], Y[g], Z[g]); for (int w = 0; w < 8; w++) bad += one[w] != enc[g][w]; }
+    return bad;
+}
 
 void hs_sha256(const uint8_t* msg, uint64_t len, uint8_t out[32]) { uint32_t st[8]; sha256_msg(st, msg, len); for (int i = 0; i < 8; i++) store_be32(out + 4 * i, st[i]); }
 void hs_hmac_sha256(const uint8_t* key, uint32_t klen, const uint8_t* msg, uint64_t len, uint8_t out[32]) {

@@ -494,6 +494,42 @@ def test_merkle_audit_proofs_match_rfc6962(ctx):
         t.close()
 
 
+def test_merkle_consistency_proofs_match_rfc6962(ctx):
+    """RFC 6962 §2.1.2 consistency proofs read out of the device tree == the published CT vectors and the oracle's recursive
+    construction; the device verifier (RFC 9162 §2.1.4.2) accepts them and rejects tampered ones."""
+    from agentfield_b200.audit import MerkleTree, verify_consistency_batch
+    g = golden("rfc6962.json")
+    hs = [OM.leaf_hash(bytes.fromhex(x)) for x in g["leaves"]]
+    for c in g["consistency"]:
+        t = MerkleTree(np.frombuffer(b"".join(hs[:c["second"]]), dtype=np.uint8), ctx)
+        assert [x.hex() for x in t.consistency_proof(c["first"])] == c["proof"], c
+        ok = verify_consistency_batch([c["first"]], [bytes.fromhex(g["roots"][c["first"] - 1])], c["second"],
+                                      bytes.fromhex(g["roots"][c["second"] - 1]), [[bytes.fromhex(x) for x in c["proof"]]], ctx)
+        assert ok.all(), c
+        t.close()
+    rng = np.random.default_rng(0xAF63)
+    for n in (1, 2, 3, 5, 8, 13, 64, 100, 1000, 4097):
+        hs = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(n)]
+        t = MerkleTree(np.frombuffer(b"".join(hs), dtype=np.uint8), ctx)
+        firsts = sorted({1, n, max(1, n // 2), max(1, n - 1), max(1, n // 3), min(n, 4), min(n, 7)})
+        proofs = [t.consistency_proof(m) for m in firsts]
+        roots = [OM.root_from_leaf_hashes(hs[:m]) for m in firsts]
+        for m, p, r in zip(firsts, proofs, roots):
+            assert p == OM.consistency_proof(hs, m), (n, m)
+            assert OM.verify_consistency(m, n, r, t.root, p)
+        assert verify_consistency_batch(firsts, roots, n, t.root, proofs, ctx).all(), n
+        bad_roots = [bytes(32)] * len(firsts)
+        got = verify_consistency_batch(firsts, bad_roots, n, t.root, proofs, ctx)
+        assert not got.any(), n
+        if n > 3:
+            # dropping a node, a wrong new root, or a size outside (0, n] must all fail; first == n only passes with an empty proof
+            cut = [p[:-1] if p else [bytes(32)] for p in proofs]
+            assert not verify_consistency_batch(firsts, roots, n, t.root, cut, ctx).any()
+            assert not verify_consistency_batch(firsts, roots, n, bytes(32), proofs, ctx).any()
+            assert not verify_consistency_batch([0, n + 1], [roots[0], roots[0]], n, t.root, [[], []], ctx).any()
+        t.close()
+
+
 def test_device_text_codecs(ctx):
     """base64url (no padding) and lowercase hex of fixed-size records == Go's base64.RawURLEncoding / hex.EncodeToString."""
     import base64
@@ -552,6 +588,16 @@ def test_full_size_verify_properties_config2(ctx):
     pk_h, sg_h, ms_h = d_pks[:m].cpu().numpy(), d_sigs[:m].cpu().numpy(), d_msgs[:m].cpu().numpy()
     off_h = np.arange(m + 1, dtype=np.uint64) * 512
     assert (CO.ed25519_verify_batch(pk_h, sg_h, ms_h.reshape(-1), off_h, 8) == d_ok[:m].cpu().numpy()).all()
+    # the host-buffer call (chunked H2D / compute / D2H ring, several chunks, a ragged last one) returns the same bitmap,
+    # with a cold issuer-key cache (tables built while the first chunk is in flight) and with a warm one
+    nh = 300_017
+    pk_h, sg_h = d_pks[:nh].cpu().numpy(), d_sigs[:nh].cpu().numpy()
+    ms_h = d_msgs[:nh].cpu().numpy().reshape(-1)
+    off_h = np.arange(nh + 1, dtype=np.uint64) * 512
+    ctx.keycache_clear(); torch.cuda.synchronize()
+    for _ in range(2):
+        got = ctx.verify_packed(pk_h, sg_h, ms_h, off_h)
+        assert (np.asarray(got).astype(np.uint8) == expect[:nh].cpu().numpy()).all()
 
 
 def test_full_size_hmac_properties_config3(ctx):

@@ -106,3 +106,18 @@ def test_keyed_table_path_logic_vs_golden(hostsim):
     for e in es:
         pk, msg, sig = (bytes.fromhex(e[k]) for k in ("pk", "msg", "sig"))
         assert hostsim.hs_verify_keyed(pk, msg, C.c_uint64(len(msg)), sig) == int(e["valid"]), e["name"]
+
+
+def test_base_point_table_chunks(hostsim):
+    """What each device thread builds at afc_init (its own start point by double-and-add, then a run of consecutive
+    multiples) equals the row-by-row construction the other hostsim checks (sign / verify vs RFC 8032) run on."""
+    w = hostsim.hs_base_window()
+    assert w in (8, 16)
+    rows, cols = 256 // w, 1 << (w - 1)
+    for i, j0 in [(0, 0), (0, cols - 64), (1, 64), (rows // 2, (cols // 2) & ~63), (rows - 1, cols - 64)]:
+        assert hostsim.hs_base_chunk_mismatches(i, j0) == 0, (i, j0)
+
+
+def test_group_encoding_shares_one_inversion(hostsim):
+    for G in range(1, 9):
+        assert hostsim.hs_encode_group_mismatches(G, 1234 + G) == 0, G

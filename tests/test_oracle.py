@@ -130,6 +130,27 @@ def test_merkle_frontier_and_inclusion_proofs():
             assert not M.verify_inclusion(hs[(m + 1) % len(hs)], m, n, M.inclusion_proof(hs[:n], m), r) or n == 1 and False
 
 
+def test_merkle_consistency_proofs():
+    """RFC 6962 §2.1.2 proofs: the published CT vectors, and construction (recursive) vs verification (RFC 9162 iterative)."""
+    g = golden("rfc6962.json")
+    hs = [M.leaf_hash(bytes.fromhex(x)) for x in g["leaves"]]
+    for c in g["consistency"]:
+        assert [x.hex() for x in M.consistency_proof(hs[:c["second"]], c["first"])] == c["proof"]
+    rng = np.random.default_rng(8)
+    hs = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(41)]
+    for n in range(1, 42):
+        rn = M.root_from_leaf_hashes(hs[:n])
+        for m in range(1, n + 1):
+            p = M.consistency_proof(hs[:n], m)
+            rm = M.root_from_leaf_hashes(hs[:m])
+            assert M.verify_consistency(m, n, rm, rn, p), (m, n)
+            if p:
+                assert not M.verify_consistency(m, n, rm, rn, p[:-1])
+                assert not M.verify_consistency(m, n, rm, rn, [bytes(32)] + p[1:])
+            assert not M.verify_consistency(m, n, bytes(32), rn, p)
+    assert not M.verify_consistency(0, 5, bytes(32), bytes(32), [])
+
+
 def test_reference_flow_vectors():
     """Key derivation, did:key, hashData and a VC-shaped canonical message (did_service.go:515-536,
     vc_service.go:434-515)."""
