@@ -26,6 +26,7 @@ constexpr int kLanes = 4;                 // concurrent host-buffer calls per co
 constexpr int kSlots = 4;                 // chunks in flight per call: copies keep streaming while an earlier chunk computes
 constexpr uint32_t kChunkItems = 1u << 17;  // items per pipeline chunk for host-buffer calls (one full wave of the table-driven verify at G = 2)
 constexpr size_t kChunkBytes = 96u << 20;   // and at most this many message bytes per chunk
+constexpr uint32_t kMinChunkItems = 1u << 14;
 
 struct DevBuf {
     uint8_t* p = nullptr;
@@ -278,7 +279,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     const bool pin_a = A.a ? is_pinned(A.a) : true, pin_b = A.b ? is_pinned(A.b) : true;
     const bool pin_keys = A.keys ? is_pinned(A.keys) : true, pin_koff = A.koff ? is_pinned(A.koff) : true;
     const bool pin_ki = A.key_index ? is_pinned(A.key_index) : true;
-    CallLog lc(ctx, 2 * (int)(A.n / kChunkItems + 2) + 8);
+    CallLog lc(ctx, 12 * (int)(A.n / kChunkItems + 8) + 8);
     uint32_t i0 = 0;
     int which = 0;
     struct Pending { uint32_t i0, cnt; bool active; } pend[kSlots] = {};
@@ -293,7 +294,13 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     while (i0 < A.n) {
         uint32_t i1 = i0;
         uint64_t base = A.off[i0];
-        while (i1 < A.n && (i1 - i0) < kChunkItems && (A.off[i1 + 1] - base <= kChunkBytes || i1 == i0)) i1++;
+        // chunks taper towards the end of the call (each takes at most half of what is left, down to kMinChunkItems): what
+        // remains to be done after the last H2D copy lands — the part of a transfer-bound call that nothing overlaps — is small
+        const uint32_t left = A.n - i0;
+        uint32_t limit = left <= kMinChunkItems ? left : (left + 1) / 2;
+        if (limit < kMinChunkItems) limit = kMinChunkItems;
+        if (limit > kChunkItems) limit = kChunkItems;
+        while (i1 < A.n && (i1 - i0) < limit && (A.off[i1 + 1] - base <= kChunkBytes || i1 == i0)) i1++;
         uint32_t cnt = i1 - i0;
         uint64_t mbytes = A.off[i1] - base;
         Slot& sl = lane.slot[which];

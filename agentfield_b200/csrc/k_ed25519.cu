@@ -83,6 +83,12 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
 // G in [1, KC_GMAX] so that the last wave is full (1 M credentials on 148 SMs x 512 threads: G = 4 is 3.3 waves = 82 % busy,
 // G = 7 is 1.9 waves = 94 % busy with a smaller inversion share).
 constexpr int KC_GMAX = 8;
+#ifndef AFC_KP_SMEM_DIGITS
+#define AFC_KP_SMEM_DIGITS 0
+#endif
+#ifndef AFC_CACHED_MINB
+#define AFC_CACHED_MINB 3
+#endif
 
 // Shared body: thread t of T handles credentials t, t + T, t + 2T, ... (G of them; lanes stay adjacent in memory).
 // lookup(i, atab) -> false when credential i's key is unknown or does not decode (ok = 0, arithmetic skipped).
@@ -92,6 +98,12 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
+#if AFC_KP_SMEM_DIGITS
+    __shared__ uint32_t s_dig[ED_THREADS][17];          // recoded scalars of the credential in flight (stride 17: conflict-free)
+    uint32_t* const dig = s_dig[threadIdx.x];
+#else
+    uint32_t* const dig = nullptr;
+#endif
     uint32_t good = 0;
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
@@ -105,7 +117,7 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
         load_words8(sig + 8, sigs + 64ull * i + 32);
         load_words8(k, (const uint8_t*)(ks + 8ull * i));
         if (!ed25519_sig_wellformed(sig)) continue;
-        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, atab, base);
+        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, atab, base, dig);
         good |= 1u << g;
     }
     uint32_t enc[KC_GMAX][8];
@@ -149,7 +161,7 @@ k_ed_hram_keyed(const uint8_t* __restrict__ key_pks, const uint32_t* __restrict_
     store_words8((uint8_t*)(k_out + 8ull * i), k);
 }
 
-__global__ void __launch_bounds__(ED_THREADS, 3)
+__global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                   const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
                   const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
@@ -270,7 +282,7 @@ k_kc_build(KeyCacheDev kc) {
 }
 // (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
 // the register allocation of the curve loop around and nothing overlaps that did not already.)
-__global__ void __launch_bounds__(ED_THREADS, 3)
+__global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
                    uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
     if (!kc.state[1]) return;
