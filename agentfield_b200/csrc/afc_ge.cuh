@@ -362,6 +362,23 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
     return ok;
 }
 
+// Prefetch policy of the table-driven loop (AFC_KP_PREFETCH: 0 none, 1 both tables into L1, 2 both into L2, 3 key table L1 /
+// base table L2).
+#ifndef AFC_KP_PREFETCH
+#define AFC_KP_PREFETCH 1
+#endif
+#define AFC_PF_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define AFC_PF_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#if AFC_KP_PREFETCH == 2
+#define AFC_PREFETCH_A(p) AFC_PF_L2(p)
+#define AFC_PREFETCH_B(p) AFC_PF_L2(p)
+#elif AFC_KP_PREFETCH == 3
+#define AFC_PREFETCH_A(p) AFC_PF_L1(p)
+#define AFC_PREFETCH_B(p) AFC_PF_L2(p)
+#else
+#define AFC_PREFETCH_A(p) AFC_PF_L1(p)
+#define AFC_PREFETCH_B(p) AFC_PF_L1(p)
+#endif
 // R' = [S]B + [k](-A) through the two tables, left in projective form (X : Y : Z): 32 mixed additions from the key's
 // radix-256 table of -A and 256/W from the base-point table, no doublings.
 template <class F = FeInline>
@@ -380,13 +397,13 @@ AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const 
     for (int i = 0; i < COMB_ROWS; i++) {
         int dk = sc_digit256(kt, i);
         int ds = (i & ((1 << SH) - 1)) ? 0 : sc_digit_base(st, i >> SH);
-#if AFC_DEVICE_CODE
+#if AFC_DEVICE_CODE && AFC_KP_PREFETCH
         if (i + 1 < COMB_ROWS) {       // the next rows' entries are random 96-byte reads (HBM / L2): start them now
             int nk = sc_digit256(kt, i + 1), mk = nk < 0 ? -nk : nk;
-            if (mk) { const char* p = (const char*)&atab[(i + 1) * COMB_COLS + (mk - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+            if (mk) { const char* p = (const char*)&atab[(i + 1) * COMB_COLS + (mk - 1)]; AFC_PREFETCH_A(p); AFC_PREFETCH_A(p + 95); }
             if (!((i + 1) & ((1 << SH) - 1))) {
                 int ns = sc_digit_base(st, (i + 1) >> SH), ms = ns < 0 ? -ns : ns;
-                if (ms) { const char* p = (const char*)&base[(size_t)((i + 1) >> SH) * BASE_COLS + (ms - 1)]; asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 95)); }
+                if (ms) { const char* p = (const char*)&base[(size_t)((i + 1) >> SH) * BASE_COLS + (ms - 1)]; AFC_PREFETCH_B(p); AFC_PREFETCH_B(p + 95); }
             }
         }
 #endif
