@@ -340,25 +340,63 @@ AFC_HD int ed25519_verify_core(const uint32_t* pk, const uint32_t* sig, const ui
 //
 // One row of a key's table per thread: row[j] = (j+1) * 256^i * (-A), affine precomputed form.  Returns 0 if the key
 // does not decode (Go: verification with that key is always false).
+#ifndef AFC_KEYROW_CHUNK
+#define AFC_KEYROW_CHUNK 64      // measured per 1024 keys: 16 -> 2.44 ms, 32 -> 2.19 ms, 64 -> 2.05 ms (8 KB of thread-local scratch)
+#endif
+// One row from its base point P = 256^i (-A): 128 consecutive multiples, converted to affine one chunk at a time with ONE
+// field inversion per chunk (Montgomery's trick): 2 inversions per row instead of 128.
+template <class F = FeInline>
+AFC_HD void ge_key_row_from_base(ge_precomp* row, const ge_p3& P) {
+    ge_cached c;
+    ge_p3_to_cached<F>(c, P);
+    ge_p3 M = P;
+    constexpr int CH = AFC_KEYROW_CHUNK;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COMB_COLS; c0 += CH) ge_affine_run<F, CH>(row + c0, M, c);
+}
+// A slice of a row: entries c0 .. c0+CH-1 = (c0+1 .. c0+CH) P, from the row's base point P (several threads per row: the
+// slice's start point costs ~7 doublings and an addition, and one more inversion per slice).
+template <class F, int CH>
+AFC_HD void ge_key_row_slice(ge_precomp* row, const ge_p3& P, int c0) {
+    ge_cached c;
+    ge_p3_to_cached<F>(c, P);
+    ge_p3 M;
+    ge_small_multiple<F>(M, P, c, (uint32_t)c0 + 1);
+    ge_affine_run<F, CH>(row + c0, M, c);
+}
+// The 32 row base points of one key, bases[i] = 256^i (-A): ONE doubling chain per key (248 doublings) instead of one per row
+// (8 i doublings in row i: 3968 per key, and lanes of a warp that finish at different times).
+template <class F = FeInline>
+AFC_HD int ge_key_row_bases(ge_p3* bases, const uint32_t* pk) {
+    ge_p3 P;
+    int ok = ge_frombytes<F>(P, pk);
+    fe_neg(P.X, P.X); fe_neg(P.T, P.T);
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int i = 0; i < COMB_ROWS; i++) {
+        bases[i] = P;
+        if (i + 1 < COMB_ROWS) {
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) {
+                ge_dbl<F>(t, P.X, P.Y, P.Z);
+                if (k < 7) { ge_p2 q; ge_p1p1_to_p2<F>(q, t); fe_copy(P.X, q.X); fe_copy(P.Y, q.Y); fe_copy(P.Z, q.Z); }   // T only where it is kept
+                else ge_p1p1_to_p3<F>(P, t);
+            }
+        }
+    }
+    return ok;
+}
+// Single-thread form (one row, its own doubling chain): what the first build of the cache did; kept as the independent check
+// of the two-step construction in tests/hostsim.
 template <class F = FeInline>
 AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
-    ge_p3 P, M;
+    ge_p3 P;
     int ok = ge_frombytes<F>(P, pk);
     fe_neg(P.X, P.X); fe_neg(P.T, P.T);
     ge_p1p1 t;
 #pragma unroll 1
     for (int k = 0; k < 8 * i; k++) { ge_dbl<F>(t, P.X, P.Y, P.Z); ge_p1p1_to_p3<F>(P, t); }
-    ge_cached c;
-    ge_p3_to_cached<F>(c, P);
-    M = P;
-    // 128 consecutive multiples, converted to affine one chunk at a time with ONE field inversion per chunk (Montgomery's
-    // trick): 2 inversions per row instead of 128.
-#ifndef AFC_KEYROW_CHUNK
-#define AFC_KEYROW_CHUNK 64      // measured per 1024 keys: 16 -> 2.44 ms, 32 -> 2.19 ms, 64 -> 2.05 ms (8 KB of thread-local scratch)
-#endif
-    constexpr int CH = AFC_KEYROW_CHUNK;
-#pragma unroll 1
-    for (int c0 = 0; c0 < COMB_COLS; c0 += CH) ge_affine_run<F, CH>(row + c0, M, c);
+    ge_key_row_from_base<F>(row, P);
     return ok;
 }
 

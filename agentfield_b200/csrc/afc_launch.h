@@ -71,6 +71,7 @@ struct KeyCache {
     void* tabs;             // max_keys x 32 x 128 ge_precomp
     uint32_t* state;        // 8 words: [0] cached keys [1] mode [2] reset pending [3] distinct [4] to build [5] snapshot [6] missing
     uint32_t* build_list;   // max_keys
+    void* bases;            // max_keys x 32 ge_p3: row base points of the tables being built in this call (indexed by build position)
     uint32_t* bslots;       // per-call: batch de-duplication table (bmask + 1 entries, >= 2n)
     uint32_t bmask;
     uint32_t* rep;          // per-call: n
@@ -84,7 +85,8 @@ struct KeyCache {
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                             uint32_t n, uint8_t* ok, uint32_t* scratch_k, const KeyCache* kc, cudaStream_t s, LaunchLog* lg);
 size_t ed_key_table_bytes(uint32_t n_keys);
-cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg);
+size_t ed_key_bases_bytes(uint32_t n_keys);     // scratch for ed_build_key_tables
+cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                                   uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);

@@ -164,7 +164,7 @@ struct CallLog {
 // ---- issuer-key cache management ------------------------------------------------------------------------------
 void kc_free(afc_ctx* ctx) {
     launch::KeyCache& k = ctx->kc;
-    void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.state, k.build_list, k.bslots, k.rep, k.kid};
+    void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.state, k.build_list, k.bases, k.bslots, k.rep, k.kid};
     for (void* p : ps) if (p) cudaFree(p);
     if (k.side) cudaStreamDestroy(k.side);
     if (k.ev_fork) cudaEventDestroy(k.ev_fork);
@@ -184,6 +184,7 @@ const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
         bool ok = cudaMalloc((void**)&k.slots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.cpks, (size_t)k.max_keys * 32) == cudaSuccess &&
                   cudaMalloc((void**)&k.valid, k.max_keys) == cudaSuccess && cudaMalloc(&k.tabs, launch::ed_key_table_bytes(k.max_keys)) == cudaSuccess &&
                   cudaMalloc((void**)&k.state, 8 * 4) == cudaSuccess && cudaMalloc((void**)&k.build_list, (size_t)k.max_keys * 4) == cudaSuccess &&
+                  cudaMalloc(&k.bases, launch::ed_key_bases_bytes(k.max_keys)) == cudaSuccess &&
                   cudaMemset(k.slots, 0xff, (size_t)cap * 4) == cudaSuccess && cudaMemset(k.state, 0, 8 * 4) == cudaSuccess &&
                   cudaMemset(k.valid, 0, k.max_keys) == cudaSuccess &&
                   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess &&
@@ -652,11 +653,14 @@ int afc_keyset_new(afc_ctx* ctx, const uint8_t* pks, uint32_t n_keys, afc_keyset
     if (e == cudaSuccess) e = cudaMalloc((void**)&ks->d_valid, n_keys);
     if (e == cudaSuccess) e = cudaMalloc(&ks->d_tabs, ks->tab_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(ks->d_pks, pks, (size_t)n_keys * 32, cudaMemcpyHostToDevice);
+    void* d_bases = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&d_bases, launch::ed_key_bases_bytes(n_keys));
     if (e == cudaSuccess) {
         CallLog lc(ctx);
-        e = launch::ed_build_key_tables(ks->d_pks, n_keys, ks->d_tabs, ks->d_valid, 0, lc);
+        e = launch::ed_build_key_tables(ks->d_pks, n_keys, ks->d_tabs, ks->d_valid, d_bases, 0, lc);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
+    if (d_bases) cudaFree(d_bases);
     if (e != cudaSuccess) {
         set_err(ctx, e, "afc_keyset_new");
         afc_keyset_free(ks);

@@ -134,15 +134,32 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
         ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
     }
 }
-__global__ void __launch_bounds__(ED_THREADS)
-k_ed_key_rows(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_precomp* __restrict__ tabs, uint8_t* __restrict__ valid) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_keys * COMB_ROWS) return;
-    uint32_t key = t / COMB_ROWS, row = t % COMB_ROWS;
+// Per-key tables are built in two steps: one thread per key walks the doubling chain and leaves the 32 row base points
+// 256^i (-A) in scratch (latency-bound, a handful of warps: it hides behind whatever else is running), then one thread per row
+// turns its base point into 128 affine entries — uniform work, no doublings.  (One thread per row doing its own 8 i doublings:
+// 2.05 ms per 1024 keys, lanes of a warp idle for up to 248 doublings.)
+#ifndef AFC_BASES_FE
+#define AFC_BASES_FE FeInline      // the chain is latency-bound (one warp per 32 keys): inlined multiplies let the 4 squarings of a doubling overlap
+#endif
+__global__ void __launch_bounds__(32)
+k_ed_key_bases(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_p3* __restrict__ bases, uint8_t* __restrict__ valid) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
     uint32_t pk[8];
     load_words8(pk, pks + 32ull * key);
-    int ok = ge_build_key_row<FeCall>(tabs + ((size_t)key * COMB_ROWS + row) * COMB_COLS, pk, (int)row);
-    if (row == 0) valid[key] = (uint8_t)ok;
+    valid[key] = (uint8_t)ge_key_row_bases<AFC_BASES_FE>(bases + (size_t)key * COMB_ROWS, pk);
+}
+#ifndef AFC_KEYROW_PARTS
+#define AFC_KEYROW_PARTS 4          // threads per table row in the second step (128 / PARTS entries and one inversion each)
+#endif
+constexpr int KR_PARTS = AFC_KEYROW_PARTS, KR_SLICE = COMB_COLS / KR_PARTS;
+__global__ void __launch_bounds__(32)
+k_ed_key_rows(uint32_t n_keys, const ge_p3* __restrict__ bases, ge_precomp* __restrict__ tabs) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keys * COMB_ROWS * KR_PARTS) return;
+    uint32_t r = t / KR_PARTS, part = t % KR_PARTS;
+    ge_p3 P = bases[r];
+    ge_key_row_slice<FeCall, KR_SLICE>(tabs + (size_t)r * COMB_COLS, P, (int)part * KR_SLICE);
 }
 
 __global__ void __launch_bounds__(ED_THREADS)
@@ -270,15 +287,23 @@ k_kc_insert(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
     kc.kid[i] = id;
     kc.build_list[atomicAdd(&kc.state[4], 1u)] = id;
 }
-__global__ void __launch_bounds__(ED_THREADS)
-k_kc_build(KeyCacheDev kc) {
+__global__ void __launch_bounds__(32)
+k_kc_bases(KeyCacheDev kc) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!kc.state[1] || t >= kc.state[4] * COMB_ROWS) return;
-    uint32_t id = kc.build_list[t / COMB_ROWS], row = t % COMB_ROWS;
+    if (!kc.state[1] || t >= kc.state[4]) return;
+    uint32_t id = kc.build_list[t];
     uint32_t pk[8];
     load_words8(pk, kc.cpks + 32ull * id);
-    int ok = ge_build_key_row<FeCall>((ge_precomp*)kc.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS, pk, (int)row);
-    if (row == 0) kc.valid[id] = (uint8_t)ok;
+    kc.valid[id] = (uint8_t)ge_key_row_bases<AFC_BASES_FE>((ge_p3*)kc.bases + (size_t)t * COMB_ROWS, pk);
+}
+__global__ void __launch_bounds__(32)
+k_kc_build(KeyCacheDev kc) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!kc.state[1] || t >= kc.state[4] * COMB_ROWS * KR_PARTS) return;
+    uint32_t r = t / KR_PARTS, part = t % KR_PARTS;
+    uint32_t id = kc.build_list[r / COMB_ROWS], row = r % COMB_ROWS;
+    ge_p3 P = ((const ge_p3*)kc.bases)[r];
+    ge_key_row_slice<FeCall, KR_SLICE>((ge_precomp*)kc.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS, P, (int)part * KR_SLICE);
 }
 // (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
 // the register allocation of the curve loop around and nothing overlaps that did not already.)
@@ -541,7 +566,10 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         if (max_build)
             // one warp per CTA: 32 x keys small CTAs spread evenly over the 148 SMs (128-thread CTAs left half of them with
             // twice the work of the rest: 2.44 ms vs the arithmetic floor of ~1.4 ms for 1024 keys)
-            AFC_LAUNCH(lg, "k_kc_build", q, k_kc_build<<<blocks_for(max_build * COMB_ROWS, 32), 32, 0, q>>>(kc));
+        {
+            AFC_LAUNCH(lg, "k_kc_bases", q, k_kc_bases<<<blocks_for(max_build, 32), 32, 0, q>>>(kc));
+            AFC_LAUNCH(lg, "k_kc_build", q, k_kc_build<<<blocks_for(max_build * COMB_ROWS * KR_PARTS, 32), 32, 0, q>>>(kc));
+        }
         if ((e = cudaEventRecord(kc.ev_join, q)) != cudaSuccess) return e;
         AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
         if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
@@ -559,9 +587,11 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
     return cudaGetLastError();
 }
 size_t ed_key_table_bytes(uint32_t n_keys) { return sizeof(ge_precomp) * (size_t)n_keys * COMB_ROWS * COMB_COLS; }
-cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, cudaStream_t s, LaunchLog* lg) {
+size_t ed_key_bases_bytes(uint32_t n_keys) { return sizeof(ge_p3) * (size_t)n_keys * COMB_ROWS; }
+cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg) {
     if (n_keys == 0) return cudaSuccess;
-    AFC_LAUNCH(lg, "k_ed_key_rows", s, k_ed_key_rows<<<blocks_for((uint64_t)n_keys * COMB_ROWS, 32), 32, 0, s>>>(pks, n_keys, (ge_precomp*)tabs, valid));
+    AFC_LAUNCH(lg, "k_ed_key_bases", s, k_ed_key_bases<<<blocks_for(n_keys, 32), 32, 0, s>>>(pks, n_keys, (ge_p3*)bases_scratch, valid));
+    AFC_LAUNCH(lg, "k_ed_key_rows", s, k_ed_key_rows<<<blocks_for((uint64_t)n_keys * COMB_ROWS * KR_PARTS, 32), 32, 0, s>>>(n_keys, (const ge_p3*)bases_scratch, (ge_precomp*)tabs));
     return cudaGetLastError();
 }
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,

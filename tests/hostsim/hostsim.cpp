@@ -50,6 +50,23 @@ int hs_base_chunk_mismatches(int i, int j0) {
     return bad;
 }
 int hs_base_window(void) { return BASE_W; }
+// words in which row i of a key's table built by the two-step construction differs from the single-thread form
+int hs_key_row_mismatches(const uint8_t pk[32], int i) {
+    uint32_t p[8]; words_from_bytes(p, pk, 8);
+    static ge_precomp a[COMB_COLS], b[COMB_COLS];
+    ge_p3 bases[COMB_ROWS];
+    int ok1 = ge_key_row_bases(bases, p);
+    for (int part = 0; part < 4; part++) ge_key_row_slice<FeInline, COMB_COLS / 4>(a, bases[i], part * (COMB_COLS / 4));   // as k_kc_build does
+    int ok2 = ge_build_key_row(b, p, i);
+    int bad = ok1 != ok2;
+    for (int j = 0; j < COMB_COLS; j++) {
+        uint32_t x[8], y[8];
+        const fe* u[3] = {&a[j].ypx, &a[j].ymx, &a[j].xy2d};
+        const fe* v[3] = {&b[j].ypx, &b[j].ymx, &b[j].xy2d};
+        for (int q = 0; q < 3; q++) { fe_towords(x, *u[q]); fe_towords(y, *v[q]); for (int w = 0; w < 8; w++) bad += x[w] != y[w]; }
+    }
+    return bad;
+}
 // ge_encode_group (one inversion for G points, run-time G) against ge_encode point by point; returns mismatching words
 int hs_encode_group_mismatches(int G, uint32_t seed) {
     ensure_tables();
@@ -122,8 +139,10 @@ int hs_verify_keyed(const uint8_t pk[32], const uint8_t* msg, uint64_t len, cons
     words_from_bytes(p, pk, 8); words_from_bytes(s, sig, 16);
     if (cached_ok < 0 || memcmp(cached_pk, pk, 32) != 0) {
         atab.resize(COMB_ROWS * COMB_COLS);
-        int ok = 1;
-        for (int i = 0; i < COMB_ROWS; i++) ok &= ge_build_key_row(&atab[i * COMB_COLS], p, i);
+        // the device's two-step construction: one doubling chain for the 32 row base points, then each row from its base
+        ge_p3 bases[COMB_ROWS];
+        int ok = ge_key_row_bases(bases, p);
+        for (int i = 0; i < COMB_ROWS; i++) ge_key_row_from_base(&atab[i * COMB_COLS], bases[i]);
         cached_ok = ok; memcpy(cached_pk, pk, 32);
     }
     ed25519_hram(k, p, s, msg, len);

@@ -121,3 +121,10 @@ def test_base_point_table_chunks(hostsim):
 def test_group_encoding_shares_one_inversion(hostsim):
     for G in range(1, 9):
         assert hostsim.hs_encode_group_mismatches(G, 1234 + G) == 0, G
+
+
+def test_key_table_two_step_build_equals_single_thread_rows(hostsim):
+    """Row base points from one doubling chain (T dropped between doublings) + rows from their bases == each row from A."""
+    pk = bytes.fromhex(golden("rfc8032.json")[0]["pk"])
+    for i in (0, 1, 7, 31):
+        assert hostsim.hs_key_row_mismatches(pk, i) == 0, i
