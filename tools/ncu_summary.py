@@ -27,7 +27,7 @@ def main():
         col.setdefault(h, i)
     out = {}
     for r in rows[2:]:
-        name = r[col["Kernel Name"]].split("(")[0]
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
         print(name)
         rec = {}
         for w in WANT:
@@ -37,7 +37,8 @@ def main():
             v = float(r[i].replace(",", ""))
             print("   %s = %f %s" % (w, v, units[i]))
             rec[w] = v * SCALE.get(units[i], 1.0) if units[i] in SCALE else v
-        out[name] = rec
+        if name not in out or rec.get("gpu__time_duration.sum", 0) > out[name].get("gpu__time_duration.sum", 0):
+            out[name] = rec                      # several launches of one kernel (tree levels): keep the longest
         print()
     if "--update-traffic" in sys.argv:
         path = sys.argv[sys.argv.index("--update-traffic") + 1]
