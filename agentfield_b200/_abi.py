@@ -79,6 +79,8 @@ SYMBOLS = {
     "afc_comm_destroy": (C.c_int, [vp]),
     "afc_b64url_encode_fixed_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
     "afc_hex_encode_fixed_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "afc_json_fill_sizes_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, u64p, vp]),
+    "afc_json_fill_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp]),
     "afc_ingest_new": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "afc_ingest_free": (None, [vp]),
     "afc_ingest_submit": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, u64p]),

@@ -608,6 +608,30 @@ int afc_hex_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_by
 }
 
 
+int afc_json_fill_sizes_dev(afc_ctx* ctx, const uint8_t* d_segs, const uint32_t* d_seg_off, const uint8_t* d_kinds, uint32_t n_fields,
+                            const uint8_t* d_fields, const uint64_t* d_field_off, uint32_t n, uint64_t* d_out_off, uint64_t* total_bytes, void* stream) {
+    DEV_PROLOGUE();
+    if (!d_seg_off || !d_out_off || (n_fields && !d_kinds) || (n && n_fields && !d_field_off)) return AFC_EINVAL;
+    uint64_t* d_scratch = nullptr;
+    CK(cudaMallocAsync((void**)&d_scratch, launch::json_scan_scratch_bytes(n), st));
+    cudaError_t e = launch::json_fill_sizes(d_segs, d_seg_off, d_kinds, n_fields, d_fields, d_field_off, n, d_out_off, d_scratch, st, lc);
+    cudaFreeAsync(d_scratch, st);
+    CK(e);
+    if (total_bytes) {
+        CK(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    DEV_EPILOGUE();
+}
+int afc_json_fill_dev(afc_ctx* ctx, const uint8_t* d_segs, const uint32_t* d_seg_off, const uint8_t* d_kinds, uint32_t n_fields,
+                      const uint8_t* d_fields, const uint64_t* d_field_off, uint32_t n, const uint64_t* d_out_off, uint8_t* d_out, void* stream) {
+    DEV_PROLOGUE();
+    if (!d_seg_off || !d_out_off || (n && !d_out) || (n_fields && !d_kinds) || (n && n_fields && !d_field_off)) return AFC_EINVAL;
+    CK(launch::json_fill(d_segs, d_seg_off, d_kinds, n_fields, d_fields, d_field_off, n, d_out_off, d_out, st, lc));
+    DEV_EPILOGUE();
+}
+
+
 int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys) {
     if (!ctx) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));

@@ -13,6 +13,7 @@
 // roofline's ops/byte; see DESIGN.md §kernels.
 #include "afc_launch.h"
 #include "afc_sha.cuh"
+#include "afc_json.cuh"
 
 namespace afc {
 
@@ -242,6 +243,82 @@ k_merkle_verify_consistency(const uint64_t* __restrict__ first_sizes, const uint
     ok[t] = (uint8_t)(good && sn == 0 && diff == 0);
 }
 
+// ---- canonical form: n documents assembled from one template and n x F values (afc_json.cuh) ----------
+// Pass 1 writes every document's length to len_out[i] (= d_out_off + 1), an inclusive scan turns them into offsets, pass 2
+// writes the bytes.  One document per thread; reads and writes go through aligned 32-bit words.
+__global__ void __launch_bounds__(HASH_THREADS)
+k_json_sizes(const uint8_t* __restrict__ segs, const uint32_t* __restrict__ seg_off, const uint8_t* __restrict__ kinds, uint32_t F,
+             const uint8_t* __restrict__ fields, const uint64_t* __restrict__ field_off, uint32_t n, uint64_t* __restrict__ len_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ByteCounter c; c.init();
+    json_fill_one(c, segs, seg_off, kinds, F, fields, field_off + (uint64_t)i * F);
+    len_out[i] = c.n;
+}
+__global__ void __launch_bounds__(HASH_THREADS)
+k_json_fill(const uint8_t* __restrict__ segs, const uint32_t* __restrict__ seg_off, const uint8_t* __restrict__ kinds, uint32_t F,
+            const uint8_t* __restrict__ fields, const uint64_t* __restrict__ field_off, uint32_t n, const uint64_t* __restrict__ out_off,
+            uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ByteWriter w; w.init(out + out_off[i]);
+    json_fill_one(w, segs, seg_off, kinds, F, fields, field_off + (uint64_t)i * F);
+    w.finish();
+}
+// In-place inclusive scan of n 64-bit values: per-block scan (1024 values per 256-thread block) + block totals, an exclusive
+// scan of the totals by one block, and a final add.
+constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 4, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(uint64_t* __restrict__ v, uint64_t n, uint64_t* __restrict__ tile_sums) {
+    __shared__ uint64_t warp_tot[SCAN_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_PER_THREAD;
+    uint64_t x[SCAN_PER_THREAD], run = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) { x[k] = (base + k < n) ? v[base + k] : 0; run += x[k]; x[k] = run; }
+    uint64_t incl = run;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += y; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint64_t before = 0;
+    for (unsigned w = 0; w < warp; w++) before += warp_tot[w];
+    const uint64_t excl = before + incl - run;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) if (base + k < n) v[base + k] = x[k] + excl;
+    if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = before + incl;
+}
+__global__ void __launch_bounds__(1024)
+k_scan_tile_sums(uint64_t* __restrict__ tile_sums, uint64_t n_tiles) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t b = 0; b < n_tiles; b += 1024) {
+        const uint64_t i = b + threadIdx.x;
+        const uint64_t x = i < n_tiles ? tile_sums[i] : 0;
+        uint64_t incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += y; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint64_t before = carry;
+        for (unsigned w = 0; w < warp; w++) before += warp_tot[w];
+        if (i < n_tiles) tile_sums[i] = before + incl - x;             // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint64_t* __restrict__ v, uint64_t n, const uint64_t* __restrict__ tile_sums) {
+    const uint64_t add = tile_sums[blockIdx.x];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) if (base + k < n) v[base + k] += add;
+}
+
 // ---- text codecs either side of the kernels: base64url without padding for signatures / digests
 // (base64.RawURLEncoding in vc_service.go:465,514) and lowercase hex for the webhook header (hex.EncodeToString,
 // webhook_dispatcher.go:473).  Fixed-size records; one thread per 3-byte group / per byte pair.
@@ -350,6 +427,24 @@ cudaError_t merkle_verify_consistency(const uint64_t* first_sizes, const uint8_t
                                       const uint8_t* proofs, const uint32_t* proof_off, uint32_t m, uint8_t* ok, cudaStream_t s, LaunchLog* lg) {
     if (m == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_merkle_verify_consistency", s, k_merkle_verify_consistency<<<blocks_for(m, HASH_THREADS), HASH_THREADS, 0, s>>>(first_sizes, first_roots, second_size, second_root, proofs, proof_off, m, ok));
+    return cudaGetLastError();
+}
+size_t json_scan_scratch_bytes(uint32_t n) { return (((size_t)n + SCAN_TILE - 1) / SCAN_TILE + 1) * 8; }
+cudaError_t json_fill_sizes(const uint8_t* segs, const uint32_t* seg_off, const uint8_t* kinds, uint32_t F, const uint8_t* fields,
+                            const uint64_t* field_off, uint32_t n, uint64_t* out_off, uint64_t* scan_scratch, cudaStream_t s, LaunchLog* lg) {
+    cudaError_t e = cudaMemsetAsync(out_off, 0, 8, s);
+    if (e != cudaSuccess || n == 0) return e;
+    const uint32_t tiles = blocks_for(n, SCAN_TILE);
+    AFC_LAUNCH(lg, "k_json_sizes", s, k_json_sizes<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(segs, seg_off, kinds, F, fields, field_off, n, out_off + 1));
+    AFC_LAUNCH(lg, "k_scan_tiles", s, k_scan_tiles<<<tiles, SCAN_THREADS, 0, s>>>(out_off + 1, n, scan_scratch));
+    AFC_LAUNCH(lg, "k_scan_tile_sums", s, k_scan_tile_sums<<<1, 1024, 0, s>>>(scan_scratch, tiles));
+    AFC_LAUNCH(lg, "k_scan_add", s, k_scan_add<<<tiles, SCAN_THREADS, 0, s>>>(out_off + 1, n, scan_scratch));
+    return cudaGetLastError();
+}
+cudaError_t json_fill(const uint8_t* segs, const uint32_t* seg_off, const uint8_t* kinds, uint32_t F, const uint8_t* fields,
+                      const uint64_t* field_off, uint32_t n, const uint64_t* out_off, uint8_t* out, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_json_fill", s, k_json_fill<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(segs, seg_off, kinds, F, fields, field_off, n, out_off, out));
     return cudaGetLastError();
 }
 cudaError_t b64url_encode(const uint8_t* in, uint32_t item, uint32_t n, uint8_t* out, cudaStream_t s, LaunchLog* lg) {

@@ -54,6 +54,18 @@ class ExpandedKeys:
         buf, off = pack(msgs)
         return [bytes(s) for s in self.ctx.sign_expanded_packed(self._expanded, ki, buf, off)]
 
+    def sign_dev(self, dids, d_msgs, d_off, n):
+        """The same for messages already on the device (e.g. assembled there by canonical.JsonTemplate.fill_dev)."""
+        import torch
+        dev = d_off.device
+        ki = np.fromiter((self._index[d] for d in dids), dtype=np.uint32, count=len(dids))
+        d_exp = torch.from_numpy(self._expanded).to(dev)
+        d_ki = torch.from_numpy(ki.view(np.int32)).to(dev)
+        d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        self.ctx.sign_expanded_dev(d_exp, d_ki, d_msgs, d_off, n, d_sigs)
+        torch.cuda.synchronize(dev)
+        return [bytes(s) for s in d_sigs.cpu().numpy()]
+
 
 class KeySet:
     """afc_keyset: issuer public keys with device-resident verification tables (384 KB per key)."""

@@ -7,7 +7,8 @@
 
 Same names (snake_cased) and behaviour; each takes a BATCH (the natural seam is the loop in
 VerifyWorkflowVCComprehensive, vc_service.go:1442-1512, or a linger queue in front of one-per-request calls) and does
-every hash / signature on the GPU through the C ABI.  JSON canonicalisation is host work (go_json.py).
+every hash / signature on the GPU through the C ABI.  The canonical JSON bytes come from go_json.py on the host or, with
+canonical_on_device=True, from the device template (canonical.py): values -> documents -> signatures without a host round trip.
 """
 import base64
 
@@ -42,10 +43,12 @@ def generate_webhook_signature_batch(secrets, bodies, ctx=None):
 class VCService:
     """Batched issue / verify of execution VCs over a key cache (DID -> expanded key) and an issuer key set."""
 
-    def __init__(self, keys: ExpandedKeys, ctx=None, hash_sensitive_data=True):
+    def __init__(self, keys: ExpandedKeys, ctx=None, hash_sensitive_data=True, canonical_on_device=False):
         self.ctx = ctx or keys.ctx
         self.keys = keys
         self.hash_sensitive_data = hash_sensitive_data
+        self.canonical_on_device = canonical_on_device
+        self._templates = None
         self._keyset = None
         self._keyset_dids = None
 
@@ -83,13 +86,30 @@ class VCService:
                 },
             }
             docs.append(doc)
-            msgs.append(go_json.vc_document(doc))                                        # zero-valued proof: what signVC signs
-        sigs = self.keys.sign_batch([r["caller_did"] for r in requests], msgs)           # one GPU batch
+            if not self.canonical_on_device:
+                msgs.append(go_json.vc_document(doc))                                    # zero-valued proof: what signVC signs
+        dids = [r["caller_did"] for r in requests]
+        if self.canonical_on_device and n:
+            import torch
+            from . import canonical
+            if self._templates is None:
+                self._templates = (canonical.vc_document_template(False, self.ctx), canonical.vc_document_template(True, self.ctx))
+            t0, t1 = self._templates
+            dev = torch.device("cuda", self.ctx.device)
+            fields, off = t0.pack_values([canonical.vc_document_values(d) for d in docs])
+            d_msgs, d_off = t0.fill_dev(torch.from_numpy(fields).to(dev), torch.from_numpy(off.view(np.int64)).to(dev), n)
+            sigs = self.keys.sign_dev(dids, d_msgs, d_off, n)                            # documents never leave the device
+        else:
+            sigs = self.keys.sign_batch(dids, msgs)                                      # one GPU batch
+        proofs = [{"type": "Ed25519Signature2020", "created": r["proof_created"], "verificationMethod": "%s#key-1" % r["caller_did"],
+                   "proofPurpose": "assertionMethod", "proofValue": _b64url(sig)} for r, sig in zip(requests, sigs)]
+        if self.canonical_on_device and n:
+            stored = self._templates[1].fill([canonical.vc_document_values(d, p) for d, p in zip(docs, proofs)])
+        else:
+            stored = [go_json.vc_document(d, p) for d, p in zip(docs, proofs)]
         out = []
-        for r, doc, sig in zip(requests, docs, sigs):
-            proof = {"type": "Ed25519Signature2020", "created": r["proof_created"], "verificationMethod": "%s#key-1" % r["caller_did"],
-                     "proofPurpose": "assertionMethod", "proofValue": _b64url(sig)}
-            out.append({"vc_document": go_json.vc_document(doc, proof), "signature": proof["proofValue"],
+        for doc, proof, vc_bytes in zip(docs, proofs, stored):
+            out.append({"vc_document": vc_bytes, "signature": proof["proofValue"],
                         "input_hash": doc["credentialSubject"]["execution"]["inputHash"],
                         "output_hash": doc["credentialSubject"]["execution"]["outputHash"], "doc": doc, "proof": proof})
         return out

@@ -532,6 +532,28 @@ def extras(ctx, dev, world, rank):
     ms_m = min(append_ms() for _ in range(3))
     aud.close()
     out["merkle_append_64B_leaves"] = {"leaves_per_s": n / (ms_m * 1e-3), "ms": ms_m}
+    # canonical form on the device: 2^19 VCDocument-shaped documents (23 values of 32 bytes, 6 % of them bytes Go escapes)
+    try:
+        from agentfield_b200 import canonical as CA
+        tmpl = CA.vc_document_template(False, ctx)
+        F, flen = tmpl.n_fields, 32
+        table = torch.tensor(list(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-_:/") + [0x22, 0x3c, 0x0a, 0x5c], dtype=torch.uint8, device=dev)
+        d_vals = table[torch.randint(0, table.numel(), (n * F * flen,), device=dev, generator=torch.Generator(device=dev).manual_seed(5))]
+        d_voff = torch.arange(n * F + 1, device=dev, dtype=torch.int64) * flen
+        # RAW members must be valid JSON on their own: digits for the numeric / pre-rendered ones
+        kinds = torch.tensor(tmpl.kinds, device=dev)
+        raw_cols = torch.nonzero(kinds == CA.RAW).flatten()
+        v2 = d_vals.view(n, F, flen)
+        v2[:, raw_cols, :] = 0x31
+        d_doc, d_doff = tmpl.fill_dev(d_vals, d_voff, n)
+        ms_c = timed(lambda: tmpl.fill_dev(d_vals, d_voff, n), reps=3)
+        total = int(d_doff[-1].item())
+        out["canonical_form_vc_documents"] = {"docs_per_s": n / (ms_c * 1e-3), "ms": ms_c, "bytes_out": total, "bytes_in": int(d_vals.numel()),
+                                              "hbm_frac": (total + d_vals.numel() * 2 + 8 * (n * F + n)) / (ms_c * 1e-3) / 1e9 / hbm_peak,
+                                              "note": "sizes pass + scan + fill pass + the host read of the total size; values read twice"}
+        del d_doc, d_doff, d_vals, d_voff, v2
+    except Exception as ex:
+        out["canonical_form_vc_documents"] = {"error": repr(ex)}
     if world > 1:
         from agentfield_b200 import shard
         roots = shard.allgather_roots(bytes(root_dev.cpu().tolist()))

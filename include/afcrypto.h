@@ -198,6 +198,24 @@ int afc_comm_destroy(afc_ctx* ctx);
 int afc_b64url_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream);
 int afc_hex_encode_fixed_dev(afc_ctx* ctx, const uint8_t* d_in, uint32_t item_bytes, uint32_t n, uint8_t* d_out, void* stream);
 
+/* ---- canonical form on the device ---------------------------------------------------------------
+ * What the reference signs is json.Marshal of a fixed struct (VCDocument pkg/types/did_types.go:135-220; marshalled at
+ * internal/services/vc_service.go:436-439 for signing and :201 for storage; ExecutionWebhookPayload pkg/types/webhook.go:42-53,
+ * marshalled at internal/services/webhook_dispatcher.go:286-300): constant text interleaved with a fixed number of values.
+ * n documents out[i] = seg[0] || v(i,0) || seg[1] || ... || v(i,F-1) || seg[F]; v(i,f) = d_fields[d_field_off[i*F+f] .. [i*F+f+1])
+ * written according to d_kinds[f]: AFC_JSON_STRING = Go encoding/json string escaping (HTML-safe; U+2028/9; invalid UTF-8
+ * becomes \ufffd byte by byte) without the quotes — the template supplies them; AFC_JSON_RAW = copied (numbers, pre-rendered
+ * optional members).  d_seg_off: F+2 offsets into d_segs.  afc_json_fill_sizes_dev leaves the n+1 output offsets in
+ * d_out_off (and, if total_bytes is not NULL, synchronises and returns the total); afc_json_fill_dev writes the bytes. */
+#define AFC_JSON_STRING 0
+#define AFC_JSON_RAW 1
+int afc_json_fill_sizes_dev(afc_ctx* ctx, const uint8_t* d_segs, const uint32_t* d_seg_off, const uint8_t* d_kinds, uint32_t n_fields,
+                            const uint8_t* d_fields, const uint64_t* d_field_off, uint32_t n, uint64_t* d_out_off, uint64_t* total_bytes,
+                            void* stream);
+int afc_json_fill_dev(afc_ctx* ctx, const uint8_t* d_segs, const uint32_t* d_seg_off, const uint8_t* d_kinds, uint32_t n_fields,
+                      const uint8_t* d_fields, const uint64_t* d_field_off, uint32_t n, const uint64_t* d_out_off, uint8_t* d_out,
+                      void* stream);
+
 /* ---- N2: batching ingest dispatcher (BASELINE.json configs[4]: sustained mixed ingest) ------------------------------
  * One "agent action" = Ed25519 signature over the credential bytes (expanded key `key_index` of the identity cache) +
  * HMAC-SHA256 webhook tag + one audit-log leaf (the signature) appended to an RFC 6962 log owned by the dispatcher.

@@ -8,6 +8,7 @@
 // agentfield_b200/ loads this library.
 #define AFC_HOSTSIM 1
 #include "../../agentfield_b200/csrc/afc_ge.cuh"
+#include "../../agentfield_b200/csrc/afc_json.cuh"
 
 #include <vector>
 
@@ -50,6 +51,19 @@ int hs_base_chunk_mismatches(int i, int j0) {
     return bad;
 }
 int hs_base_window(void) { return BASE_W; }
+// Go-JSON escaping of one string (the device routine, afc_json.cuh): returns the escaped length; writes it if out != NULL
+uint64_t hs_json_escape(const uint8_t* s, uint64_t len, uint8_t* out) {
+    ByteCounter c; c.init(); go_json_escape(c, s, len);
+    if (out) { ByteWriter w; w.init(out); go_json_escape(w, s, len); w.finish(); }
+    return c.n;
+}
+// one document from a template (what one thread of k_json_sizes / k_json_fill does)
+uint64_t hs_json_fill_one(const uint8_t* segs, const uint32_t* seg_off, const uint8_t* kinds, uint32_t F, const uint8_t* fields,
+                          const uint64_t* foff, uint8_t* out) {
+    ByteCounter c; c.init(); json_fill_one(c, segs, seg_off, kinds, F, fields, foff);
+    if (out) { ByteWriter w; w.init(out); json_fill_one(w, segs, seg_off, kinds, F, fields, foff); w.finish(); }
+    return c.n;
+}
 // words in which row i of a key's table built by the two-step construction differs from the single-thread form
 int hs_key_row_mismatches(const uint8_t pk[32], int i) {
     uint32_t p[8]; words_from_bytes(p, pk, 8);

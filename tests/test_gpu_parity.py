@@ -344,6 +344,9 @@ def test_config1_issue_and_verify_1000_vcs_reference_flow(ctx):
         assert got["vc_document"] == exp["vc_document"] and got["signature"] == exp["signature"]
         canon_lens.add(len(exp["canonical"]))
     assert canon_lens == {1536}
+    # the same flow with the canonical bytes assembled on the device (values -> documents -> signatures, no host marshalling)
+    issued_dev = VCService(cache, ctx, canonical_on_device=True).generate_execution_vc_batch(reqs)
+    assert [(v["vc_document"], v["signature"]) for v in issued_dev] == [(v["vc_document"], v["signature"]) for v in issued]
     ok = svc.verify_vc_batch(issued)
     assert all(ok) and all(ref_vc.verify_vc(v["vc_document"], cache.public_key(v["doc"]["issuer"])) for v in issued[:50])
     # tamper: change a field of the parsed document / swap signatures
@@ -528,6 +531,61 @@ def test_merkle_consistency_proofs_match_rfc6962(ctx):
             assert not verify_consistency_batch(firsts, roots, n, bytes(32), proofs, ctx).any()
             assert not verify_consistency_batch([0, n + 1], [roots[0], roots[0]], n, t.root, [[], []], ctx).any()
         t.close()
+
+
+def test_device_canonical_form_equals_go_json(ctx):
+    """afc_json_fill_*_dev: documents assembled on the GPU from the VCDocument template == the host restatement of
+    json.Marshal (go_json.vc_document), with and without proof, for values full of characters Go escapes; raw byte strings
+    (invalid UTF-8 included) == the byte-level oracle; sizes / offsets consistent; then sign what the GPU assembled."""
+    import torch
+    from agentfield_b200 import canonical as CA, go_json as GJ
+    from oracle import go_json as OJ
+    rng = np.random.default_rng(0xAF35)
+    alphabet = list("abcXYZ019 -_:/.") + ['"', "\\", "<", ">", "&", "\n", "\t", "\r", "\b", "\f", "\x00", "\x1f", "\x7f", "é", "ß", "中", "😀", "\u2028", "\u2029"]
+
+    def word(lo=0, hi=24):
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), int(rng.integers(lo, hi))))
+
+    docs, proofs = [], []
+    for i in range(700):
+        docs.append({"@context": ["https://www.w3.org/2018/credentials/v1", word()], "type": ["VerifiableCredential", word()] if i % 5 else None,
+                     "id": "urn:agentfield:vc:" + word(), "issuer": "did:key:z" + word(1), "issuanceDate": word(),
+                     "credentialSubject": {"executionId": word(0, 200 if i % 7 == 0 else 24), "workflowId": word(), "sessionId": word(),
+                                           "caller": {"did": word(), "type": word(), "agentNodeDid": word()},
+                                           "target": {"did": word(), "agentNodeDid": word(), "functionName": word()},
+                                           "execution": {"inputHash": word(), "outputHash": word(), "timestamp": word(),
+                                                         "durationMs": int(rng.integers(0, 2**31)), "status": word(),
+                                                         "errorMessage": word(1) if i % 3 == 0 else ""},
+                                           "audit": {"inputDataHash": word(), "outputDataHash": word(),
+                                                     "metadata": {"agentfield_version": "1.0.0", word(1): word()} if i % 4 else None}}})
+        proofs.append({"type": "Ed25519Signature2020", "created": word(), "verificationMethod": word() + "#key-1", "proofPurpose": "assertionMethod",
+                       "proofValue": word()})
+    t0, t1 = CA.vc_document_template(False, ctx), CA.vc_document_template(True, ctx)
+    got0 = t0.fill([CA.vc_document_values(d) for d in docs])
+    got1 = t1.fill([CA.vc_document_values(d, p) for d, p in zip(docs, proofs)])
+    for d, p, a, b in zip(docs, proofs, got0, got1):
+        assert a == GJ.vc_document(d)
+        assert b == GJ.vc_document(d, p)
+    # byte-level: arbitrary (also invalid) UTF-8 through a 2-value template, every output alignment
+    pool = [bytes([i]) for i in range(256)] + ["中".encode(), "😀".encode(), b"\xe2\x80\xa8", b"\xed\xa0\x80", b"\xf4\x90\x80\x80"]
+    segs, kinds = [b"[", b"|", b"]"], [CA.STRING, CA.RAW]
+    t2 = CA.JsonTemplate(segs, kinds, ctx)
+    items = [[b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 70)))),
+              b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 9))))] for _ in range(3000)]
+    got = t2.fill(items)
+    assert got == [OJ.fill_template(segs, kinds, it) for it in items]
+    assert t2.fill([]) == [] and CA.JsonTemplate([b"const"], [], ctx).fill([[], []]) == [b"const", b"const"]
+    # the assembled bytes feed the signer without leaving the device
+    dev = torch.device("cuda", 0)
+    fields, off = t0.pack_values([CA.vc_document_values(d) for d in docs])
+    d_out, d_off = t0.fill_dev(torch.from_numpy(fields).to(dev), torch.from_numpy(off.view(np.int64)).to(dev), len(docs))
+    seeds = rng.integers(0, 256, (len(docs), 32), dtype=np.uint8)
+    d_sigs = torch.empty((len(docs), 64), dtype=torch.uint8, device=dev)
+    ctx.sign_dev(torch.from_numpy(seeds).to(dev), d_out, d_off, len(docs), d_sigs)
+    torch.cuda.synchronize()
+    sigs = d_sigs.cpu().numpy()
+    for i in (0, 1, 350, 699):
+        assert sigs[i].tobytes() == CO.sign(seeds[i].tobytes(), GJ.vc_document(docs[i]))
 
 
 def test_device_text_codecs(ctx):

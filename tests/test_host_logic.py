@@ -149,3 +149,35 @@ def test_go_json_restatement_two_constructions_agree():
     wp = go_json.webhook_payload({"event": "execution.completed", "execution_id": "e", "workflow_id": "w", "status": "succeeded", "target": "n.fn",
                                   "type": "reasoner", "duration_ms": 12, "result": {"k": "<v>"}, "error_message": None, "timestamp": "t"})
     assert wp == b'{"event":"execution.completed","execution_id":"e","workflow_id":"w","status":"succeeded","target":"n.fn","type":"reasoner","duration_ms":12,"result":{"k":"\\u003cv\\u003e"},"timestamp":"t"}'
+
+
+def test_vc_document_template_matches_go_json():
+    """The constant segments + value order of the device canonical-form template reproduce json.Marshal(VCDocument) when filled
+    by the byte-level oracle (no GPU needed): checks the template itself, omitempty errorMessage, null slices, nested metadata."""
+    from agentfield_b200 import canonical as CA, go_json as GJ
+    from oracle import go_json as OJ
+    rng = np.random.default_rng(0xAF36)
+    alphabet = list("abcXYZ019 -_:/.") + ['"', "\\", "<", ">", "&", "\n", "\t", "\x00", "\x7f", "é", "中", "😀", " "]
+
+    def word(lo=0, hi=20):
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), int(rng.integers(lo, hi))))
+
+    p0, p1 = CA.vc_document_template_parts(False), CA.vc_document_template_parts(True)
+    for i in range(300):
+        doc = {"@context": [word(), word()], "type": [word()] if i % 5 else None, "id": word(), "issuer": word(), "issuanceDate": word(),
+               "credentialSubject": {"executionId": word(), "workflowId": word(), "sessionId": word(),
+                                     "caller": {"did": word(), "type": word(), "agentNodeDid": word()},
+                                     "target": {"did": word(), "agentNodeDid": word(), "functionName": word()},
+                                     "execution": {"inputHash": word(), "outputHash": word(), "timestamp": word(), "durationMs": int(rng.integers(0, 2**40)),
+                                                   "status": word(), "errorMessage": word(1) if i % 3 == 0 else ""},
+                                     "audit": {"inputDataHash": word(), "outputDataHash": word(), "metadata": {word(1): word(), "k": [1, word()]} if i % 4 else None}}}
+        proof = {"type": word(), "created": word(), "verificationMethod": word(), "proofPurpose": word(), "proofValue": word()}
+        assert OJ.fill_template(p0[0], p0[1], CA.vc_document_values(doc)) == GJ.vc_document(doc)
+        assert OJ.fill_template(p1[0], p1[1], CA.vc_document_values(doc, proof)) == GJ.vc_document(doc, proof)
+    # the webhook payload template (HMAC input, W1)
+    wp = CA.webhook_payload_template_parts()
+    for i in range(100):
+        pl = {"event": word(), "execution_id": word(), "workflow_id": word(), "status": word(), "target": word(), "type": word(),
+              "duration_ms": int(rng.integers(0, 10**6)) if i % 2 else None, "result": {"a": word(), "b": [1, 2.5, None]} if i % 3 else None,
+              "error_message": word() if i % 5 == 0 else None, "timestamp": word()}
+        assert OJ.fill_template(wp[0], wp[1], CA.webhook_payload_values(pl)) == GJ.webhook_payload(pl)

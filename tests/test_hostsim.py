@@ -128,3 +128,53 @@ def test_key_table_two_step_build_equals_single_thread_rows(hostsim):
     pk = bytes.fromhex(golden("rfc8032.json")[0]["pk"])
     for i in (0, 1, 7, 31):
         assert hostsim.hs_key_row_mismatches(pk, i) == 0, i
+
+
+def test_go_json_escaping_and_template_fill(hostsim):
+    """Device routine for Go encoding/json string escaping (afc_json.cuh) vs the byte-level oracle: every single byte, every
+    byte pair around the UTF-8 boundaries, random strings at every alignment, and documents assembled from a template."""
+    from oracle import go_json as OJ
+    hostsim.hs_json_escape.restype = C.c_uint64
+    hostsim.hs_json_fill_one.restype = C.c_uint64
+
+    def dev_escape(raw, al=0):
+        keep, ptr = _placed(raw, al)
+        n = hostsim.hs_json_escape(ptr, C.c_uint64(len(raw)), None)
+        out = np.zeros(n + 8, dtype=np.uint8)
+        a0 = (-out.ctypes.data) % 4
+        assert hostsim.hs_json_escape(ptr, C.c_uint64(len(raw)), C.cast(out.ctypes.data + a0 + (al % 4), C.POINTER(C.c_uint8))) == n
+        return out[a0 + (al % 4):a0 + (al % 4) + n].tobytes()
+
+    for b in range(256):
+        assert dev_escape(bytes([b])) == OJ.escape_bytes(bytes([b])), b
+    edge = [0x00, 0x1f, 0x20, 0x22, 0x5c, 0x7f, 0x80, 0x9f, 0xa0, 0xbf, 0xc0, 0xc1, 0xc2, 0xdf, 0xe0, 0xe2, 0xec, 0xed, 0xee, 0xef, 0xf0, 0xf4, 0xf5, 0xff,
+            0x8f, 0x90, 0xa8, 0xa9]
+    for a in edge:
+        for b in edge:
+            for tail in (b"", b"\x80", b"\x80\x80", b"\xa8", b"\xbf\xbf\x41"):
+                raw = bytes([a, b]) + tail
+                assert dev_escape(raw) == OJ.escape_bytes(raw), raw
+    rng = np.random.default_rng(0xAF34)
+    pool = [bytes([i]) for i in range(128)] + ["é".encode(), "中".encode(), "😀".encode(), b"\xe2\x80\xa8", b"\xe2\x80\xa9", b"\xff", b"\xc3", b"\xed\xa0\x80"]
+    for t in range(300):
+        raw = b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 60))))
+        assert dev_escape(raw, t % 16) == OJ.escape_bytes(raw), raw
+    # template: {"a":"<v0>","n":<v1>,"b":"<v2>"}
+    segs = [b'{"a":"', b'","n":', b',"b":"', b'"}']
+    kinds = [OJ.STRING, OJ.RAW, OJ.STRING]
+    sb = np.frombuffer(b"".join(segs), dtype=np.uint8).copy()
+    so = np.zeros(len(segs) + 1, dtype=np.uint32); so[1:] = np.cumsum([len(x) for x in segs])
+    kk = np.array(kinds, dtype=np.uint8)
+    for t in range(100):
+        vals = [b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 30)))), str(int(rng.integers(0, 10**9))).encode(),
+                b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 30))))]
+        fb = np.frombuffer(b"".join(vals) + b"\0", dtype=np.uint8).copy()
+        fo = np.zeros(len(vals) + 1, dtype=np.uint64); fo[1:] = np.cumsum([len(x) for x in vals])
+        want = OJ.fill_template(segs, kinds, vals)
+        args = (sb.ctypes.data_as(C.c_void_p), so.ctypes.data_as(C.c_void_p), kk.ctypes.data_as(C.c_void_p), C.c_uint32(len(vals)),
+                fb.ctypes.data_as(C.c_void_p), fo.ctypes.data_as(C.c_void_p))
+        n = hostsim.hs_json_fill_one(*args, None)
+        assert n == len(want)
+        out = np.zeros(n + 4, dtype=np.uint8)
+        hostsim.hs_json_fill_one(*args, out.ctypes.data_as(C.c_void_p))
+        assert out[:n].tobytes() == want
