@@ -43,13 +43,33 @@ struct ByteWriter {
         acc |= b << (8 * n);
         if (++n == 4) { *(uint32_t*)p = acc; p += 4; acc = 0; n = 0; }
     }
+    // four bytes at once (little-endian word): one aligned store, whatever the phase of the pending bytes
+    AFC_HDM void put4(uint32_t x) {
+        if (head) { put(x & 0xff); put((x >> 8) & 0xff); put((x >> 16) & 0xff); put(x >> 24); return; }
+        *(uint32_t*)p = acc | (n ? x << (8 * n) : x);
+        p += 4;
+        acc = n ? x >> (32 - 8 * n) : 0;
+    }
     AFC_HDM void finish() { for (uint32_t k = 0; k < n; k++) *p++ = (uint8_t)(acc >> (8 * k)); n = 0; acc = 0; }
 };
 struct ByteCounter {
     uint64_t n;
     AFC_HDM void init() { n = 0; }
     AFC_HDM void put(uint32_t) { ++n; }
+    AFC_HDM void put4(uint32_t) { n += 4; }
 };
+
+// 1 iff each of the four bytes of x is written unchanged by Go's encoder: 0x20..0x7f and none of  " \\ < > &
+// (SWAR: "some byte is zero" = (v - 0x01010101) & ~v & 0x80808080;  < and > differ in bit 1,  " and & in bit 2)
+AFC_HD uint32_t json_word_is_plain(uint32_t x) {
+    const uint32_t H = 0x80808080u, L = 0x01010101u;
+    uint32_t bad = x & H;                                            // >= 0x80
+    bad |= (x - 0x20202020u) & ~x & H;                               // < 0x20
+    uint32_t v = (x | 0x02020202u) ^ 0x3e3e3e3eu; bad |= (v - L) & ~v & H;      // < >
+    v = (x | 0x04040404u) ^ 0x26262626u; bad |= (v - L) & ~v & H;               // " &
+    v = x ^ 0x5c5c5c5cu; bad |= (v - L) & ~v & H;                               // backslash
+    return bad == 0;
+}
 
 AFC_HD uint32_t json_hex_digit(uint32_t v) { return v < 10 ? '0' + v : 'a' + (v - 10); }
 
@@ -75,6 +95,10 @@ AFC_HD void go_json_escape(Sink& out, const uint8_t* s, uint64_t len) {
     ByteWindow w; w.init(s, len);
     while (w.rem) {
         w.fill();
+        if (w.rem >= 4 && w.have >= 4) {                        // four plain bytes at a time (DIDs, hashes, timestamps: the common case)
+            const uint32_t x = (uint32_t)w.win;
+            if (json_word_is_plain(x)) { out.put4(x); w.skip(4); continue; }
+        }
         const uint32_t b = w.peek(0);
         if (b < 0x80) {
             if (b >= 0x20 && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { out.put(b); w.skip(1); continue; }
@@ -115,6 +139,7 @@ AFC_HD void json_copy_raw(Sink& out, const uint8_t* s, uint64_t len) {
     ByteWindow w; w.init(s, len);
     while (w.rem) {
         w.fill();
+        if (w.rem >= 4 && w.have >= 4) { out.put4((uint32_t)w.win); w.skip(4); continue; }
         uint32_t k = w.have < w.rem ? w.have : (uint32_t)w.rem;
         for (uint32_t j = 0; j < k; j++) out.put(w.peek(j));
         w.skip(k);

@@ -159,6 +159,20 @@ def test_go_json_escaping_and_template_fill(hostsim):
     for t in range(300):
         raw = b"".join(pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(0, 60))))
         assert dev_escape(raw, t % 16) == OJ.escape_bytes(raw), raw
+    # long plain runs (the four-bytes-at-a-time path) broken by single special / multi-byte characters, every input alignment and
+    # every phase of the output word
+    plain = bytes(b for b in range(0x20, 0x80) if b not in b'"\\<>&')
+    for t in range(400):
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            parts.append(bytes(plain[int(i)] for i in rng.integers(0, len(plain), int(rng.integers(0, 41)))))
+            parts.append(pool[int(rng.integers(0, len(pool)))] if rng.integers(0, 4) else b"")
+        raw = b"".join(parts)
+        assert dev_escape(raw, t % 16) == OJ.escape_bytes(raw), raw
+    for b in range(256):                                   # one odd byte at each position of an otherwise plain word
+        for pos in range(4):
+            raw = b"abcdefgh"[:pos] + bytes([b]) + b"ijklmnop"
+            assert dev_escape(raw, pos) == OJ.escape_bytes(raw), raw
     # template: {"a":"<v0>","n":<v1>,"b":"<v2>"}
     segs = [b'{"a":"', b'","n":', b',"b":"', b'"}']
     kinds = [OJ.STRING, OJ.RAW, OJ.STRING]
