@@ -420,12 +420,8 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
 // R' = [S]B + [k](-A) through the two tables, left in projective form (X : Y : Z): 32 mixed additions from the key's
 // radix-256 table of -A and 256/W from the base-point table, no doublings.
 template <class F = FeInline>
-AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* base,
-                                uint32_t* digits = nullptr) {
-    // the recoded scalars are read one digit per iteration: callers short of registers pass 16 words of (shared) memory for them
-    uint32_t kt_r[8], st_r[8];
-    uint32_t* kt = digits ? digits : kt_r;
-    uint32_t* st = digits ? digits + 8 : st_r;
+AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const uint32_t* k, const ge_precomp* atab, const ge_precomp* base) {
+    uint32_t kt[8], st[8];
     sc_recode256(kt, k);
     sc_recode_base(st, sig + 8);
     constexpr int SH = BASE_W == 16 ? 1 : 0;            // the base table advances one row every 2^SH rows of the key table

@@ -33,24 +33,55 @@ struct ByteWindow {
     AFC_HDM void skip(uint32_t k) { win = k >= 8 ? 0 : win >> (8 * k); have -= k; rem -= k; }
 };
 
-// Byte sink that writes aligned 32-bit words (single bytes only for an unaligned head and the tail).
+// Byte sink that writes aligned 16-byte blocks (single bytes only for an unaligned head; words and bytes for the tail): with
+// one document per thread a warp's store touches 32 different lines whatever its width, so wider stores are fewer line accesses.
+#ifndef AFC_JSON_WIDE_STORES
+#define AFC_JSON_WIDE_STORES 1
+#endif
 struct ByteWriter {
-    uint8_t* p;
-    uint32_t acc, n, head;
-    AFC_HDM void init(uint8_t* dst) { p = dst; acc = 0; n = 0; head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3); }
+    uint8_t* p;                 // next store address (once head == 0)
+    uint32_t acc, n, head;      // word being assembled: n bytes in acc
+    uint32_t s0, s1, s2, wi;    // words of the current 16-byte block already complete (the fourth goes straight out)
+    AFC_HDM void init(uint8_t* dst) {
+        p = dst; acc = 0; n = 0; wi = 0; s0 = s1 = s2 = 0;
+        head = (uint32_t)(((AFC_JSON_WIDE_STORES ? 16 : 4) - ((uintptr_t)dst & (AFC_JSON_WIDE_STORES ? 15 : 3))) & (AFC_JSON_WIDE_STORES ? 15 : 3));
+    }
+    AFC_HDM void word(uint32_t x) {
+#if AFC_JSON_WIDE_STORES
+        if (wi == 0) s0 = x; else if (wi == 1) s1 = x; else if (wi == 2) s2 = x;
+        else {
+#if AFC_DEVICE_CODE
+            *(uint4*)p = make_uint4(s0, s1, s2, x);
+#else
+            uint32_t v[4] = {s0, s1, s2, x}; memcpy(p, v, 16);
+#endif
+            p += 16; wi = 0; return;
+        }
+        ++wi;
+#else
+        *(uint32_t*)p = x; p += 4;
+#endif
+    }
     AFC_HDM void put(uint32_t b) {
         if (head) { *p++ = (uint8_t)b; --head; return; }
         acc |= b << (8 * n);
-        if (++n == 4) { *(uint32_t*)p = acc; p += 4; acc = 0; n = 0; }
+        if (++n == 4) { word(acc); acc = 0; n = 0; }
     }
-    // four bytes at once (little-endian word): one aligned store, whatever the phase of the pending bytes
+    // four bytes at once (little-endian word), whatever the phase of the pending bytes
     AFC_HDM void put4(uint32_t x) {
         if (head) { put(x & 0xff); put((x >> 8) & 0xff); put((x >> 16) & 0xff); put(x >> 24); return; }
-        *(uint32_t*)p = acc | (n ? x << (8 * n) : x);
-        p += 4;
+        word(acc | (n ? x << (8 * n) : x));
         acc = n ? x >> (32 - 8 * n) : 0;
     }
-    AFC_HDM void finish() { for (uint32_t k = 0; k < n; k++) *p++ = (uint8_t)(acc >> (8 * k)); n = 0; acc = 0; }
+    AFC_HDM void finish() {
+        uint32_t* q = (uint32_t*)p;
+        if (wi > 0) q[0] = s0;
+        if (wi > 1) q[1] = s1;
+        if (wi > 2) q[2] = s2;
+        uint8_t* t = p + 4 * wi;
+        for (uint32_t k = 0; k < n; k++) t[k] = (uint8_t)(acc >> (8 * k));
+        n = 0; acc = 0; wi = 0;
+    }
 };
 struct ByteCounter {
     uint64_t n;

@@ -80,14 +80,11 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
 // ---- keyed verification (identity cache): per-key radix-256 tables of -A, built once per key set
 // Credentials per thread in the table-driven kernels (they share ONE field inversion, Montgomery's trick).  The group size is a
 // launch parameter: every thread does the same work, so a launch runs in whole waves of `resident threads`; pick_group() chooses
-// G in [1, KC_GMAX] so that the last wave is full (1 M credentials on 148 SMs x 512 threads: G = 4 is 3.3 waves = 82 % busy,
-// G = 7 is 1.9 waves = 94 % busy with a smaller inversion share).
+// G in [1, KC_GMAX] so that the last wave is full and the inversion share small (1 M credentials on 148 SMs x 512 threads: G = 7,
+// 1.9 waves, 4.21 ms; fixed G = 4, 3.3 waves, 4.35 ms; a 65 536-credential chunk of a host call: G = 1, one wave).
 constexpr int KC_GMAX = 8;
-#ifndef AFC_KP_SMEM_DIGITS
-#define AFC_KP_SMEM_DIGITS 0
-#endif
 #ifndef AFC_CACHED_MINB
-#define AFC_CACHED_MINB 3
+#define AFC_CACHED_MINB 3      // 5 (96 registers, 20 warps/SM) was measured: 4.5 ms, spills
 #endif
 
 // Shared body: thread t of T handles credentials t, t + T, t + 2T, ... (G of them; lanes stay adjacent in memory).
@@ -98,12 +95,6 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
-#if AFC_KP_SMEM_DIGITS
-    __shared__ uint32_t s_dig[ED_THREADS][17];          // recoded scalars of the credential in flight (stride 17: conflict-free)
-    uint32_t* const dig = s_dig[threadIdx.x];
-#else
-    uint32_t* const dig = nullptr;
-#endif
     uint32_t good = 0;
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
@@ -117,7 +108,7 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
         load_words8(sig + 8, sigs + 64ull * i + 32);
         load_words8(k, (const uint8_t*)(ks + 8ull * i));
         if (!ed25519_sig_wellformed(sig)) continue;
-        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, atab, base, dig);
+        ed25519_keyed_point<FeInline>(X[g], Y[g], Z[g], sig, k, atab, base);
         good |= 1u << g;
     }
     uint32_t enc[KC_GMAX][8];
