@@ -495,6 +495,33 @@ AFC_HD void ed25519_expand(uint32_t* s, uint32_t* prefix, uint32_t* pk, const ui
     ge_scalarmult_base<F>(A, sr, comb);
     ge_encode<F>(pk, A.X, A.Y, A.Z);
 }
+// The two halves of signing either side of the point encodings, for kernels that share ONE field inversion between the
+// encodings of several credentials (and of A = [s]B when signing from seeds):
+//   seed -> (s clamped, prefix)                               NewKeyFromSeed without the public key
+AFC_HD void ed25519_expand_scalar(uint32_t* s, uint32_t* prefix, const uint32_t* seed) {
+    uint32_t dig[16];
+    sha512_prefixed<8>(dig, seed, (const uint8_t*)0, 0);
+    dig[0] &= 0xfffffff8u;
+    dig[7] &= 0x3fffffffu;
+    dig[7] |= 0x40000000u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s[i] = dig[i]; prefix[i] = dig[8 + i]; }
+}
+//   r = SHA-512(prefix || M) mod L
+AFC_HD void ed25519_nonce(uint32_t* r, const uint32_t* prefix, const uint8_t* msg, uint64_t len) {
+    uint32_t dig[16];
+    sha512_prefixed<8>(dig, prefix, msg, len);
+    sc_reduce512(r, dig);
+}
+//   sig = encR || (H(encR || pk || M) s + r) mod L
+AFC_HD void ed25519_sign_finish(uint32_t* sig, const uint32_t* encR, const uint32_t* pk, const uint32_t* s, const uint32_t* r,
+                                const uint8_t* msg, uint64_t len) {
+    uint32_t k[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) sig[i] = encR[i];
+    ed25519_hram(k, pk, sig, msg, len);
+    sc_muladd(sig + 8, k, s, r);
+}
 // Sign with an expanded key (s, prefix, pk)
 template <class F = FeInline>
 AFC_HD void ed25519_sign_expanded(uint32_t* sig, const uint32_t* s, const uint32_t* prefix, const uint32_t* pk,

@@ -51,6 +51,24 @@ int hs_base_chunk_mismatches(int i, int j0) {
     return bad;
 }
 int hs_base_window(void) { return BASE_W; }
+// signing the way k_ed_sign does it: scalars first, both points ([s]B and [r]B) encoded with one shared inversion, then the rest
+void hs_sign_grouped(const uint8_t seed[32], const uint8_t* msg, uint64_t len, uint8_t sig[64]) {
+    ensure_tables();
+    uint32_t sd[8], s[8], prefix[8], sr[8], r[8], sg[16], enc[8][8];
+    words_from_bytes(sd, seed, 8);
+    ed25519_expand_scalar(s, prefix, sd);
+    sc_reduce256(sr, s);
+    ge_p3 A, R;
+    ge_scalarmult_base(A, sr, &g_comb[0]);
+    ed25519_nonce(r, prefix, msg, len);
+    ge_scalarmult_base(R, r, &g_comb[0]);
+    fe X[8], Y[8], Z[8];
+    fe_copy(X[0], R.X); fe_copy(Y[0], R.Y); fe_copy(Z[0], R.Z);
+    fe_copy(X[1], A.X); fe_copy(Y[1], A.Y); fe_copy(Z[1], A.Z);
+    ge_encode_group<FeInline, 8>(enc, X, Y, Z, 2);
+    ed25519_sign_finish(sg, enc[0], enc[1], s, r, msg, len);
+    bytes_from_words(sig, sg, 16);
+}
 // Go-JSON escaping of one string (the device routine, afc_json.cuh): returns the escaped length; writes it if out != NULL
 uint64_t hs_json_escape(const uint8_t* s, uint64_t len, uint8_t* out) {
     ByteCounter c; c.init(); go_json_escape(c, s, len);

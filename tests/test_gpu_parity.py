@@ -627,6 +627,23 @@ def test_full_size_verify_properties_config2(ctx):
     d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     ctx.sign_expanded_dev(d_exp, d_ki, d_msgs.view(-1), d_off, n, d_sigs)
     d_pks = d_exp[:, 64:][d_ki.long()].contiguous()
+    # at this size k_ed_sign shares one inversion between 4 credentials per thread (strided by T = n / 4): signatures from every
+    # stride position, and from the seed path (8 points per inversion) on a 400 000-item slice, equal the oracle's
+    ks_h = d_kseeds.cpu().numpy()
+    T4 = (n + 3) // 4
+    sample = sorted({0, 1, 31, 32, 127, 128, T4 - 1, T4, T4 + 1, 2 * T4 - 1, 2 * T4, 3 * T4, 3 * T4 + 77, n - 2, n - 1, 123457, 765432})
+    sg_h, ms_s = d_sigs[sample].cpu().numpy(), d_msgs[sample].cpu().numpy()
+    for j, i in enumerate(sample):
+        assert sg_h[j].tobytes() == CO.sign(ks_h[i % K].tobytes(), ms_s[j].tobytes()), i
+    ns = 400_000
+    d_seeds_full = d_kseeds[d_ki[:ns].long()].contiguous()
+    d_sigs2 = torch.empty((ns, 64), dtype=torch.uint8, device=dev)
+    ctx.sign_dev(d_seeds_full, d_msgs.view(-1), d_off[:ns + 1], ns, d_sigs2)
+    assert torch.equal(d_sigs2, d_sigs[:ns])
+    d_exp2 = torch.empty((ns, 96), dtype=torch.uint8, device=dev)
+    ctx.expand_dev(d_seeds_full, ns, d_exp2)                      # grouped key expansion == the 1024 keys expanded one per thread
+    assert torch.equal(d_exp2, d_exp[d_ki[:ns].long()])
+    del d_sigs2, d_seeds_full, d_exp2
     idx = torch.arange(n, device=dev)
     flip_msg = idx % 100 == 0
     flip_s = idx % 100 == 50

@@ -85,6 +85,7 @@ def test_ed25519_kernel_logic_vs_golden_and_oracle(hostsim):
         seed, pk, msg, sig = (bytes.fromhex(e[k]) for k in ("seed", "pk", "msg", "sig"))
         o = _b(32); hostsim.hs_pubkey(seed, o); assert bytes(o) == pk, e["name"]
         o = _b(64); hostsim.hs_sign(seed, msg, C.c_uint64(len(msg)), o); assert bytes(o) == sig, e["name"]
+        o = _b(64); hostsim.hs_sign_grouped(seed, msg, C.c_uint64(len(msg)), o); assert bytes(o) == sig, e["name"]   # k_ed_sign's split
         assert hostsim.hs_verify(pk, msg, C.c_uint64(len(msg)), sig) == 1
     for e in golden("ed25519_edge.json"):
         pk, msg, sig = (bytes.fromhex(e[k]) for k in ("pk", "msg", "sig"))
