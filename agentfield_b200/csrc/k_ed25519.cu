@@ -311,10 +311,10 @@ k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const ui
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index.
-// Thread t of T signs credentials t, t + T, ... (G <= SIGN_GMAX of them).  All their points — R = [r]B and, from seeds, A = [s]B —
+// Thread t of T signs credentials t, t + T, ... (G <= SIGN_GMAX of them, chosen per launch by pick_sign_group).  All their points — R = [r]B and, from seeds, A = [s]B —
 // are computed first and encoded with ONE field inversion (Montgomery's trick): per credential the inversion was 70 % of the
 // field work of a signature from an expanded key (16 mixed additions = 112 multiplications against 265) and twice that from a seed.
-constexpr int SIGN_GMAX = 4;
+constexpr int SIGN_GMAX = 8;
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, int mode,
           const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ sigs) {
@@ -544,49 +544,37 @@ namespace launch {
 
 static inline uint32_t blocks_for(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
 
-// Group size for a table-driven launch of n credentials: minimise waves(G) x (G x main + inversion), in field multiplications.
-static int pick_group(uint32_t n, const void* kernel) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("AFC_KC_GROUP"); forced = e ? atoi(e) : 0; }
-    if (forced >= 1 && forced <= KC_GMAX) return forced;
-    static thread_local int resident[2] = {0, 0};
-    static thread_local const void* which[2] = {nullptr, nullptr};
-    int slot = (which[0] == kernel || which[0] == nullptr) ? 0 : 1;
-    if (which[slot] != kernel || !resident[slot]) {
+// Group size for a launch of n credentials whose threads share one field inversion per G credentials: every thread does the
+// same work, so the launch runs in whole waves of `resident threads`; minimise waves(G) x (G x main + inversion), both in field
+// multiplications (SHA-512 work counted at its measured equivalent).
+static int pick_group_for(uint32_t n, const void* kernel, int slot, uint64_t c_main, uint64_t c_inv, int gmax, const char* env) {
+    static int forced[4] = {-1, -1, -1, -1};
+    if (forced[slot] < 0) { const char* e = getenv(env); forced[slot] = e ? atoi(e) : 0; }
+    if (forced[slot] >= 1 && forced[slot] <= gmax) return forced[slot];
+    static thread_local int resident[4] = {0, 0, 0, 0};
+    if (!resident[slot]) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ED_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 3; }
-        which[slot] = kernel; resident[slot] = sms * per_sm * ED_THREADS;
+        resident[slot] = sms * per_sm * ED_THREADS;
     }
     const uint64_t R = (uint64_t)resident[slot];
-    const uint64_t c_main = (uint64_t)(COMB_ROWS + BASE_ROWS) * 7 + 12, c_inv = 270;
     int best = 1; uint64_t best_cost = ~0ull;
-    for (int G = 1; G <= KC_GMAX; G++) {
+    for (int G = 1; G <= gmax; G++) {
         uint64_t T = ((uint64_t)n + G - 1) / G, waves = (T + R - 1) / R;
         uint64_t cost = waves * (G * c_main + c_inv);
         if (cost < best_cost) { best_cost = cost; best = G; }
     }
     return best;
 }
-
-// Credentials per thread for a signing launch: share the inversion as widely as the batch allows without leaving SMs idle
-// (a dispatcher batch of a few thousand actions keeps one credential per thread).
-static int pick_sign_group(uint32_t n) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("AFC_SIGN_GROUP"); forced = e ? atoi(e) : 0; }
-    if (forced >= 1 && forced <= SIGN_GMAX) return forced;
-    static thread_local int resident = 0;
-    if (!resident) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_ed_sign, ED_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 3; }
-        resident = sms * per_sm * ED_THREADS;
-    }
-    uint64_t g = (uint64_t)n / (uint64_t)resident;
-    return g < 1 ? 1 : g > SIGN_GMAX ? SIGN_GMAX : (int)g;
+static int pick_group(uint32_t n, const void* kernel) {          // table-driven verification: 48 mixed additions per credential
+    return pick_group_for(n, kernel, kernel == (const void*)k_ed_verify_cached ? 0 : 1, (uint64_t)(COMB_ROWS + BASE_ROWS) * 7 + 12, 270, KC_GMAX,
+                          "AFC_KC_GROUP");
 }
+// signing / key expansion: 16 mixed additions + two (one) SHA-512 passes worth ~240 (~60) multiplications of time
+static int pick_sign_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_sign, 2, 362, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
+static int pick_expand_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_expand, 3, 180, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
 
 size_t ed_tables_bytes() { return sizeof(ge_precomp) * (size_t)BASE_ROWS * BASE_COLS; }
 
@@ -680,7 +668,7 @@ cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, 
 cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
                             cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
-    const int G = pick_sign_group(n);
+    const int G = pick_expand_group(n);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
     AFC_LAUNCH(lg, "k_ed_expand", s, k_ed_expand<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, n, T, G, expanded96, pks_only));
     return cudaGetLastError();

@@ -13,6 +13,6 @@ print({k:d[k] for k in ('value','ms_per_step','steps','gpu_launches','clocks')})
 r=json.load(open('gpurun_out/bench_reference.json')); print('reference arm',r['value'],r['cpu_baseline']['cores'])
 x=json.load(open('gpurun_out/bench_extras.json'))['extras']; print({k:(v.get('ms'), v.get('p99_us')) for k,v in x.items() if k!='microbench'})"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 33 -c 66 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"^k_(ed_|hmac|sha256|merkle_leaf|merkle_level|kc_build|kc_bases)" -c 60 -o /tmp/prof_all -f python tools/ncu_targets.py > gpurun_out/ncu_all.log 2>&1
+timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"^k_(ed_|hmac|sha256|merkle_leaf|merkle_level|kc_build|kc_bases|json)" -c 64 -o /tmp/prof_all -f python tools/ncu_targets.py > gpurun_out/ncu_all.log 2>&1
 tail -2 gpurun_out/ncu_all.log
 ncu -i /tmp/prof_all.ncu-rep --page raw --csv > gpurun_out/prof_all_raw.csv 2>/dev/null; ls -la gpurun_out/prof_all_raw.csv gpurun_out/launches_final.csv

@@ -29,7 +29,16 @@ ski = (torch.arange(ns, device=dev) % bench.N_KEYS).to(torch.int32)
 sigs2 = torch.empty((ns, 64), dtype=torch.uint8, device=dev)
 soff = torch.arange(ns + 1, device=dev, dtype=torch.int64) * 64
 root = torch.empty(32, dtype=torch.uint8, device=dev)
+from agentfield_b200 import canonical as CA
+tmpl = CA.vc_document_template(False, ctx)
+plain = torch.tensor(list(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-_:/"), dtype=torch.uint8, device=dev)
+d_vals = plain[torch.randint(0, plain.numel(), (ns * tmpl.n_fields * 32,), device=dev, generator=g)]
+d_vals.view(ns, tmpl.n_fields, 32)[:, torch.nonzero(torch.tensor(tmpl.kinds, device=dev) == CA.RAW).flatten(), :] = 0x31
+d_voff = torch.arange(ns * tmpl.n_fields + 1, device=dev, dtype=torch.int64) * 32
+
+
 def one_pass():
+    tmpl.fill_dev(d_vals, d_voff, ns)                                 # k_json_sizes, k_scan_*, k_json_fill
     ctx.keycache_clear()
     ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)            # cold: k_kc_bases, k_kc_build, k_ed_hram, k_ed_verify_cached
     ks.verify_dev(d_ki, d_sigs, d_msgs, d_off, n, d_ok)               # k_ed_hram_keyed, k_ed_verify_keyed
