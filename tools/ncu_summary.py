@@ -34,7 +34,10 @@ def main():
             i = next((j for j, h in enumerate(hdr) if h == w or h.endswith("." + w)), None)
             if i is None or r[i] == "":
                 continue
-            v = float(r[i].replace(",", ""))
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:                  # "no data" (e.g. a launch that exits at once)
+                continue
             print("   %s = %f %s" % (w, v, units[i]))
             rec[w] = v * SCALE.get(units[i], 1.0) if units[i] in SCALE else v
         if name not in out or rec.get("gpu__time_duration.sum", 0) > out[name].get("gpu__time_duration.sum", 0):
