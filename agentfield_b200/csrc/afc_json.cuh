@@ -33,34 +33,30 @@ struct ByteWindow {
     AFC_HDM void skip(uint32_t k) { win = k >= 8 ? 0 : win >> (8 * k); have -= k; rem -= k; }
 };
 
-// Byte sink that writes aligned 16-byte blocks (single bytes only for an unaligned head; words and bytes for the tail): with
-// one document per thread a warp's store touches 32 different lines whatever its width, so wider stores are fewer line accesses.
-#ifndef AFC_JSON_WIDE_STORES
-#define AFC_JSON_WIDE_STORES 1
-#endif
+// Byte sink that writes aligned 32-byte blocks — one full DRAM sector per store (STG.256, sm_100) — with single bytes only for an
+// unaligned head and words + bytes for the tail.  With one document per thread a warp's store touches 32 different lines whatever
+// its width, so wider stores are fewer line accesses; and a sector written whole needs no read-for-fill (ncu, 16-byte stores:
+// 0.93 GB read + 0.76 GB written for 0.42 GB of input and 0.63 GB of output).
 struct ByteWriter {
     uint8_t* p;                 // next store address (once head == 0)
     uint32_t acc, n, head;      // word being assembled: n bytes in acc
-    uint32_t s0, s1, s2, wi;    // words of the current 16-byte block already complete (the fourth goes straight out)
+    uint32_t s0, s1, s2, s3, s4, s5, s6, wi;    // words of the current block already complete (the eighth goes straight out)
     AFC_HDM void init(uint8_t* dst) {
-        p = dst; acc = 0; n = 0; wi = 0; s0 = s1 = s2 = 0;
-        head = (uint32_t)(((AFC_JSON_WIDE_STORES ? 16 : 4) - ((uintptr_t)dst & (AFC_JSON_WIDE_STORES ? 15 : 3))) & (AFC_JSON_WIDE_STORES ? 15 : 3));
+        p = dst; acc = 0; n = 0; wi = 0; s0 = s1 = s2 = s3 = s4 = s5 = s6 = 0;
+        head = (uint32_t)((32 - ((uintptr_t)dst & 31)) & 31);
     }
     AFC_HDM void word(uint32_t x) {
-#if AFC_JSON_WIDE_STORES
-        if (wi == 0) s0 = x; else if (wi == 1) s1 = x; else if (wi == 2) s2 = x;
-        else {
+        if (wi == 7) {
 #if AFC_DEVICE_CODE
-            *(uint4*)p = make_uint4(s0, s1, s2, x);
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(x) : "memory");
 #else
-            uint32_t v[4] = {s0, s1, s2, x}; memcpy(p, v, 16);
+            uint32_t v[8] = {s0, s1, s2, s3, s4, s5, s6, x}; memcpy(p, v, 32);
 #endif
-            p += 16; wi = 0; return;
+            p += 32; wi = 0; return;
         }
+        s0 = wi == 0 ? x : s0; s1 = wi == 1 ? x : s1; s2 = wi == 2 ? x : s2; s3 = wi == 3 ? x : s3;
+        s4 = wi == 4 ? x : s4; s5 = wi == 5 ? x : s5; s6 = wi == 6 ? x : s6;
         ++wi;
-#else
-        *(uint32_t*)p = x; p += 4;
-#endif
     }
     AFC_HDM void put(uint32_t b) {
         if (head) { *p++ = (uint8_t)b; --head; return; }
@@ -75,9 +71,8 @@ struct ByteWriter {
     }
     AFC_HDM void finish() {
         uint32_t* q = (uint32_t*)p;
-        if (wi > 0) q[0] = s0;
-        if (wi > 1) q[1] = s1;
-        if (wi > 2) q[2] = s2;
+        const uint32_t st[7] = {s0, s1, s2, s3, s4, s5, s6};
+        for (uint32_t k = 0; k < wi; k++) q[k] = st[k];
         uint8_t* t = p + 4 * wi;
         for (uint32_t k = 0; k < n; k++) t[k] = (uint8_t)(acc >> (8 * k));
         n = 0; acc = 0; wi = 0;

@@ -245,10 +245,10 @@ k_merkle_verify_consistency(const uint64_t* __restrict__ first_sizes, const uint
 
 // ---- canonical form: n documents assembled from one template and n x F values (afc_json.cuh) ----------
 // Pass 1 writes every document's length to len_out[i] (= d_out_off + 1), an inclusive scan turns them into offsets, pass 2
-// writes the bytes.  One document per thread; aligned 32-bit reads, 16-byte writes, four plain bytes at a time.
-// Measured per 2^19 documents of 1.2 KB (23 values), plain / 6 % escaped bytes: sizes 0.35 / 0.90 ms, fill 0.84 / 2.23 ms.
-// Tried and dropped: 4-byte writes (fill 1.63 / 1.78 ms) and one WARP per document with one byte per lane (1.54 + 3.10 ms: a
-// 32-byte value costs a whole ballot + scan round, 47 pieces per document).
+// writes the bytes.  One document per thread; aligned 32-bit reads, 32-byte writes, four plain bytes at a time.
+// Measured per 2^19 documents of 1.2 KB (23 values), plain / 6 % escaped bytes: sizes 0.35 / 0.89 ms, fill 0.78 / 2.31 ms.
+// Tried and dropped: 4-byte writes (fill 1.63 / 1.78 ms), 16-byte writes (0.85 / 2.23 ms) and one WARP per document with one
+// byte per lane (1.54 + 3.10 ms: a 32-byte value costs a whole ballot + scan round, 47 pieces per document).
 __global__ void __launch_bounds__(HASH_THREADS)
 k_json_sizes(const uint8_t* __restrict__ segs, const uint32_t* __restrict__ seg_off, const uint8_t* __restrict__ kinds, uint32_t F,
              const uint8_t* __restrict__ fields, const uint64_t* __restrict__ field_off, uint32_t n, uint64_t* __restrict__ len_out) {
