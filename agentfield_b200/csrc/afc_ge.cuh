@@ -67,6 +67,26 @@ AFC_HD void ge_addsub(ge_p1p1& r, const ge_p3& p, const ge_cached& q, int neg) {
     fe_add(dpc, d, c); fe_sub(dmc, d, c);
     fe_select(r.Z, dpc, dmc, neg); fe_select(r.T, dmc, dpc, neg);
 }
+// One 96-byte table entry from global memory as three 256-bit loads (entries are 32-byte aligned: the tables come from cudaMalloc
+// and sizeof(ge_precomp) = 96).  Each lane gathers its own entry, so what a load costs is its 32 line accesses, not its width: left
+// to the compiler a `const ge_precomp&` becomes 24 LDG.32 — 768 L1 accesses per warp and mixed addition, more L1 time than the
+// addition has IMAD.WIDE time.
+#ifndef AFC_TABLE_LOAD256
+#define AFC_TABLE_LOAD256 1
+#endif
+AFC_HD void ge_load_precomp(ge_precomp& e, const ge_precomp* src) {
+#if AFC_DEVICE_CODE && AFC_TABLE_LOAD256
+    const uint32_t* p = (const uint32_t*)src;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.ypx.v[0]), "=r"(e.ypx.v[1]), "=r"(e.ypx.v[2]), "=r"(e.ypx.v[3]), "=r"(e.ypx.v[4]), "=r"(e.ypx.v[5]), "=r"(e.ypx.v[6]), "=r"(e.ypx.v[7]) : "l"(p));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.ymx.v[0]), "=r"(e.ymx.v[1]), "=r"(e.ymx.v[2]), "=r"(e.ymx.v[3]), "=r"(e.ymx.v[4]), "=r"(e.ymx.v[5]), "=r"(e.ymx.v[6]), "=r"(e.ymx.v[7]) : "l"(p + 8));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.xy2d.v[0]), "=r"(e.xy2d.v[1]), "=r"(e.xy2d.v[2]), "=r"(e.xy2d.v[3]), "=r"(e.xy2d.v[4]), "=r"(e.xy2d.v[5]), "=r"(e.xy2d.v[6]), "=r"(e.xy2d.v[7]) : "l"(p + 16));
+#else
+    e = *src;
+#endif
+}
 // mixed addition with an affine precomputed point
 template <class F = FeInline>
 AFC_HD void ge_maddsub(ge_p1p1& r, const ge_p3& p, const ge_precomp& q, int neg) {
@@ -216,7 +236,9 @@ AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* ba
             int neg = d < 0;
             int m = neg ? -d : d;
             ge_p1p1 r;
-            ge_maddsub<F>(r, h, base[(size_t)i * BASE_COLS + (m - 1)], neg);
+            ge_precomp e;
+            ge_load_precomp(e, &base[(size_t)i * BASE_COLS + (m - 1)]);
+            ge_maddsub<F>(r, h, e, neg);
             ge_p1p1_to_p3<F>(h, r);
         }
     }
@@ -443,12 +465,16 @@ AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const 
 #endif
         if (dk != 0) {
             int neg = dk < 0, m = neg ? -dk : dk;
-            ge_maddsub<F>(t, h, atab[i * COMB_COLS + (m - 1)], neg);
+            ge_precomp e;
+            ge_load_precomp(e, &atab[i * COMB_COLS + (m - 1)]);
+            ge_maddsub<F>(t, h, e, neg);
             ge_p1p1_to_p3<F>(h, t);
         }
         if (ds != 0) {
             int neg = ds < 0, m = neg ? -ds : ds;
-            ge_maddsub<F>(t, h, base[(size_t)(i >> SH) * BASE_COLS + (m - 1)], neg);
+            ge_precomp e;
+            ge_load_precomp(e, &base[(size_t)(i >> SH) * BASE_COLS + (m - 1)]);
+            ge_maddsub<F>(t, h, e, neg);
             ge_p1p1_to_p3<F>(h, t);
         }
     }
