@@ -308,7 +308,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         int rc = drain(which);
         if (rc != AFC_OK) return rc;
         // size buffers
-        CK(sl.msgs.reserve(mbytes + 16));
+        CK(sl.msgs.reserve(mbytes + 32));
         CK(sl.off.reserve((size_t)(cnt + 1) * 8));
         CK(sl.out.reserve((size_t)cnt * A.out_item + 16));
         if (A.a) CK(sl.a.reserve((size_t)cnt * A.a_item + 16));
@@ -335,6 +335,8 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         // same alignment whatever the chunking (d_base + off[i] == sl.msgs.p + pad + off[i] - base)
         size_t pad = (size_t)(base & 15);
         CK(h2d(sl, sl.msgs.p + pad, A.msgs + base, mbytes, pin_msgs, &used));
+        // the kernels read whole aligned words and mask what lies past a message: keep the few bytes after the last one defined
+        CK(cudaMemsetAsync(sl.msgs.p + pad + mbytes, 0, 16, sl.stream));
         CK(h2d(sl, sl.off.p, A.off + i0, (size_t)(cnt + 1) * 8, pin_off, &used));
         if (A.a) CK(h2d(sl, sl.a.p, A.a + (size_t)i0 * A.a_item, (size_t)cnt * A.a_item, pin_a, &used));
         if (A.b) CK(h2d(sl, sl.b.p, A.b + (size_t)i0 * A.b_item, (size_t)cnt * A.b_item, pin_b, &used));
@@ -346,6 +348,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         case OP_LEAF: e = launch::merkle_leaf_hashes(d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
         case OP_HMAC: {
             CK(h2d(sl, sl.a.p + (kbase & 3), A.keys + kbase, kbytes, pin_keys, &used));
+            CK(cudaMemsetAsync(sl.a.p + (kbase & 3) + kbytes, 0, 8, sl.stream));
             CK(h2d(sl, sl.koff.p, A.koff + i0, (size_t)(cnt + 1) * 4, pin_koff, &used));
             e = launch::hmac_sha256_batch(sl.a.p + (kbase & 3) - kbase, (const uint32_t*)sl.koff.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
             break;
@@ -857,6 +860,7 @@ int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf
         size_t pad = (size_t)(base & 15);
         CK(m->leaves.reserve(bytes + 32)); CK(m->off.reserve((size_t)(n + 1) * 8)); CK(m->lv[1].reserve((size_t)n * 32));
         if (bytes) CK(cudaMemcpyAsync(m->leaves.p + pad, leaves + base, bytes, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemsetAsync(m->leaves.p + pad + bytes, 0, 16, m->stream));          // words past the last leaf are read and masked
         CK(cudaMemcpyAsync(m->off.p, leaf_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, m->stream));
         CallLog lc(ctx);
         CK(launch::merkle_leaf_hashes(m->leaves.p + pad - base, (const uint64_t*)m->off.p, n, m->lv[1].p, m->stream, lc));
@@ -981,6 +985,7 @@ int afc_merkle_tree_inclusion_proofs(afc_merkle_tree* t, const uint64_t* indices
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)m * depth * 32);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_len, (size_t)m * 4);
     if (e == cudaSuccess) e = cudaMemcpy(d_idx, indices, (size_t)m * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, (size_t)m * depth * 32);             // slots past a path's length come back as zeros
     if (e == cudaSuccess) {
         CallLog lc(ctx);
         e = launch::merkle_gather_proofs((const uint8_t* const*)t->d_levels, t->d_sizes, (int)t->levels.size(), d_idx, m, d_out, d_len, 0, lc);
