@@ -37,6 +37,9 @@ struct DevBuf {
         p = nullptr; cap = 0;
         size_t want = n + n / 4 + 256;
         cudaError_t e = cudaMalloc((void**)&p, want);
+        // zeroed once: the kernels read whole aligned words and mask what lies past a message, so the slack behind the last
+        // staged byte is read (never used); this keeps those reads defined without a memset per call
+        if (e == cudaSuccess) e = cudaMemset(p, 0, want);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -335,8 +338,6 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         // same alignment whatever the chunking (d_base + off[i] == sl.msgs.p + pad + off[i] - base)
         size_t pad = (size_t)(base & 15);
         CK(h2d(sl, sl.msgs.p + pad, A.msgs + base, mbytes, pin_msgs, &used));
-        // the kernels read whole aligned words and mask what lies past a message: keep the few bytes after the last one defined
-        CK(cudaMemsetAsync(sl.msgs.p + pad + mbytes, 0, 16, sl.stream));
         CK(h2d(sl, sl.off.p, A.off + i0, (size_t)(cnt + 1) * 8, pin_off, &used));
         if (A.a) CK(h2d(sl, sl.a.p, A.a + (size_t)i0 * A.a_item, (size_t)cnt * A.a_item, pin_a, &used));
         if (A.b) CK(h2d(sl, sl.b.p, A.b + (size_t)i0 * A.b_item, (size_t)cnt * A.b_item, pin_b, &used));
@@ -348,7 +349,6 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         case OP_LEAF: e = launch::merkle_leaf_hashes(d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
         case OP_HMAC: {
             CK(h2d(sl, sl.a.p + (kbase & 3), A.keys + kbase, kbytes, pin_keys, &used));
-            CK(cudaMemsetAsync(sl.a.p + (kbase & 3) + kbytes, 0, 8, sl.stream));
             CK(h2d(sl, sl.koff.p, A.koff + i0, (size_t)(cnt + 1) * 4, pin_koff, &used));
             e = launch::hmac_sha256_batch(sl.a.p + (kbase & 3) - kbase, (const uint32_t*)sl.koff.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
             break;
@@ -860,7 +860,6 @@ int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf
         size_t pad = (size_t)(base & 15);
         CK(m->leaves.reserve(bytes + 32)); CK(m->off.reserve((size_t)(n + 1) * 8)); CK(m->lv[1].reserve((size_t)n * 32));
         if (bytes) CK(cudaMemcpyAsync(m->leaves.p + pad, leaves + base, bytes, cudaMemcpyHostToDevice, m->stream));
-        CK(cudaMemsetAsync(m->leaves.p + pad + bytes, 0, 16, m->stream));          // words past the last leaf are read and masked
         CK(cudaMemcpyAsync(m->off.p, leaf_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, m->stream));
         CallLog lc(ctx);
         CK(launch::merkle_leaf_hashes(m->leaves.p + pad - base, (const uint64_t*)m->off.p, n, m->lv[1].p, m->stream, lc));
