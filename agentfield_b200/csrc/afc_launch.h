@@ -86,6 +86,7 @@ struct KeyCache {
     cudaStream_t side;
     cudaEvent_t ev_fork, ev_join;
 };
+cudaError_t ed_keycache_clear(const KeyCache& kc, cudaStream_t s, LaunchLog* lg);     // empties the persistent table (slots, counters)
 // scratch_k: n * 32 bytes; kc: nullable (nullptr = always the generic Straus kernel)
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                             uint32_t n, uint8_t* ok, uint32_t* scratch_k, const KeyCache* kc, cudaStream_t s, LaunchLog* lg);

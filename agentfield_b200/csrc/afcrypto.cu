@@ -654,8 +654,10 @@ int afc_keycache_clear(afc_ctx* ctx, void* stream) {
     if (!ctx->kc_ready) return AFC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaStreamWaitEvent(st, ctx->kc_event, 0));
-    CK(cudaMemsetAsync(ctx->kc.slots, 0xff, ((size_t)ctx->kc.slot_mask + 1) * 4, st));
-    CK(cudaMemsetAsync(ctx->kc.state, 0, 8 * 4, st));
+    {
+        CallLog lc(ctx);
+        CK(launch::ed_keycache_clear(ctx->kc, st, lc));
+    }
     CK(cudaEventRecord(ctx->kc_event, st));
     return AFC_OK;
 }

@@ -207,6 +207,14 @@ __device__ __forceinline__ bool kc_equal(const uint32_t* a, const uint8_t* p) {
     return d == 0;
 }
 
+// Plain fills as kernels of our own: cudaMemsetAsync in these streams was measured to cost anything from microseconds to
+// ~0.7 ms per call depending on what else the driver had in flight (a 16-byte memset per staged chunk: +3.5 ms per host call).
+__global__ void __launch_bounds__(256)
+k_fill_u32(uint32_t* __restrict__ p, uint32_t v, uint64_t n) {
+    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) { *(uint4*)(p + i) = make_uint4(v, v, v, v); return; }
+    for (; i < n; i++) p[i] = v;
+}
 __global__ void k_kc_begin(KeyCacheDev kc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         kc.state[1] = 0; kc.state[3] = 0; kc.state[4] = 0; kc.state[6] = 0;
@@ -576,6 +584,13 @@ static int pick_group(uint32_t n, const void* kernel) {          // table-driven
 static int pick_sign_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_sign, 2, 362, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
 static int pick_expand_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_expand, 3, 180, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
 
+cudaError_t ed_keycache_clear(const KeyCache& kc, cudaStream_t s, LaunchLog* lg) {
+    const uint64_t cnt = (uint64_t)kc.slot_mask + 1;
+    AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for((cnt + 3) / 4, 256), 256, 0, s>>>(kc.slots, 0xffffffffu, cnt));
+    AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(kc.state, 0u, 8));
+    return cudaGetLastError();
+}
+
 size_t ed_tables_bytes() { return sizeof(ge_precomp) * (size_t)BASE_ROWS * BASE_COLS; }
 
 cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
@@ -599,8 +614,11 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         const cudaStream_t q = kc.side;
         cudaError_t e = cudaEventRecord(kc.ev_fork, s);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(q, kc.ev_fork, 0);
-        if (e == cudaSuccess) e = cudaMemsetAsync(kc.bslots, 0xff, ((size_t)kc.bmask + 1) * 4, q);
         if (e != cudaSuccess) return e;
+        {
+            const uint64_t cnt = (uint64_t)kc.bmask + 1;
+            AFC_LAUNCH(lg, "k_fill_u32", q, k_fill_u32<<<blocks_for((cnt + 3) / 4, 256), 256, 0, q>>>(kc.bslots, 0xffffffffu, cnt));
+        }
         AFC_LAUNCH(lg, "k_kc_begin", q, k_kc_begin<<<1, 32, 0, q>>>(kc));
         AFC_LAUNCH(lg, "k_kc_dedup", q, k_kc_dedup<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
         AFC_LAUNCH(lg, "k_kc_mode", q, k_kc_mode<<<1, 32, 0, q>>>(kc, n));

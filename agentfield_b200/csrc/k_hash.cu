@@ -268,6 +268,7 @@ k_json_fill(const uint8_t* __restrict__ segs, const uint32_t* __restrict__ seg_o
     json_fill_one(w, segs, seg_off, kinds, F, fields, field_off + (uint64_t)i * F);
     w.finish();
 }
+__global__ void k_set_u64(uint64_t* p, uint64_t v) { *p = v; }
 // In-place inclusive scan of n 64-bit values: per-block scan (1024 values per 256-thread block) + block totals, an exclusive
 // scan of the totals by one block, and a final add.
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 4, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
@@ -435,8 +436,8 @@ cudaError_t merkle_verify_consistency(const uint64_t* first_sizes, const uint8_t
 size_t json_scan_scratch_bytes(uint32_t n) { return (((size_t)n + SCAN_TILE - 1) / SCAN_TILE + 1) * 8; }
 cudaError_t json_fill_sizes(const uint8_t* segs, const uint32_t* seg_off, const uint8_t* kinds, uint32_t F, const uint8_t* fields,
                             const uint64_t* field_off, uint32_t n, uint64_t* out_off, uint64_t* scan_scratch, cudaStream_t s, LaunchLog* lg) {
-    cudaError_t e = cudaMemsetAsync(out_off, 0, 8, s);
-    if (e != cudaSuccess || n == 0) return e;
+    k_set_u64<<<1, 1, 0, s>>>(out_off, 0);          // (a kernel, not cudaMemsetAsync: see k_fill_u32 in k_ed25519.cu)
+    if (n == 0) return cudaGetLastError();
     const uint32_t tiles = blocks_for(n, SCAN_TILE);
     AFC_LAUNCH(lg, "k_json_sizes", s, k_json_sizes<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(segs, seg_off, kinds, F, fields, field_off, n, out_off + 1));
     AFC_LAUNCH(lg, "k_scan_tiles", s, k_scan_tiles<<<tiles, SCAN_THREADS, 0, s>>>(out_off + 1, n, scan_scratch));
