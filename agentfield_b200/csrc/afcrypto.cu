@@ -425,6 +425,15 @@ int afc_init(int device, afc_ctx** out) {
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
     if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    {   // per-call scratch comes from the stream-ordered pool: keep freed blocks across synchronisations instead of returning them to
+        // the driver (the default threshold of 0 re-maps the 32 MB of a 1 M-credential call after every sync)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     for (int l = 0; l < kLanes; l++)
         for (int s = 0; s < kSlots; s++)
             if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
