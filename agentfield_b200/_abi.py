@@ -49,6 +49,7 @@ SYMBOLS = {
     "afc_keycache_configure": (C.c_int, [vp, C.c_uint32]),
     "afc_keycache_info": (C.c_int, [vp, u32p, u32p, u32p]),
     "afc_keycache_clear": (C.c_int, [vp, vp]),
+    "afc_keycache_stats": (C.c_int, [vp, vp]),
     "afc_keyset_new": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
     "afc_keyset_free": (None, [vp]),
     "afc_keyset_info": (C.c_int, [vp, u32p, u64p]),
@@ -99,6 +100,11 @@ class IngestStats(C.Structure):
     _fields_ = [("submitted", C.c_uint64), ("completed", C.c_uint64), ("batches", C.c_uint64), ("avg_batch", C.c_double),
                 ("p50_us", C.c_uint32), ("p99_us", C.c_uint32), ("max_us", C.c_uint32), ("log_size", C.c_uint64),
                 ("log_root", C.c_uint8 * 32), ("last_error", C.c_int)]
+
+
+class KeycacheStats(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("max_keys", "cached_keys", "last_hot", "last_cold", "last_distinct", "last_built", "last_evicted",
+                                          "total_built", "total_evicted", "calls")]
 
 
 class ProfileEntry(C.Structure):

@@ -108,8 +108,49 @@ def vc_document_values(doc, proof=None):
             u(doc["issuanceDate"]), u(cs["executionId"]), u(cs["workflowId"]), u(cs["sessionId"]), u(ca["did"]), u(ca["type"]),
             u(ca["agentNodeDid"]), u(ta["did"]), u(ta["agentNodeDid"]), u(ta["functionName"]), u(ex["inputHash"]), u(ex["outputHash"]),
             u(ex["timestamp"]), b"%d" % int(ex["durationMs"]), u(ex["status"]),
-            (b',"errorMessage":' + go_json.string(em).encode("utf-8")) if em else b"",
+            (b',"errorMessage":' + go_json.any_string(em).encode("utf-8")) if em else b"",
             u(au["inputDataHash"]), u(au["outputDataHash"]), go_json.value(au.get("metadata")).encode("utf-8")]
+    if proof is not None:
+        vals += [u(proof.get("type", "")), u(proof.get("created", "")), u(proof.get("verificationMethod", "")),
+                 u(proof.get("proofPurpose", "")), u(proof.get("proofValue", ""))]
+    return vals
+
+
+def workflow_vc_document_template(with_proof=False, ctx=None):
+    """Template of json.Marshal(types.WorkflowVCDocument) on the GPU (see workflow_vc_document_template_parts)."""
+    return JsonTemplate(*workflow_vc_document_template_parts(with_proof), ctx)
+
+
+def workflow_vc_document_template_parts(with_proof=False):
+    """(segments, kinds) of json.Marshal(types.WorkflowVCDocument) (pkg/types/did_types.go:146-180; signed over a zero Proof at
+    internal/services/vc_service.go:686-693, verified the same way at :1589-1597).  componentVcIds ([]string), the two step
+    counts (int), the optional endTime (*string, omitempty) and the metadata map are pre-rendered raw values."""
+    S, R = STRING, RAW
+    parts = [('{"@context":', R), (',"type":', R), (',"id":"', S), ('","issuer":"', S), ('","issuanceDate":"', S),
+             ('","credentialSubject":{"workflowId":"', S), ('","sessionId":"', S), ('","componentVcIds":', R), (',"totalSteps":', R),
+             (',"completedSteps":', R), (',"status":"', S), ('","startTime":"', S), ('"', R),          # optional ,"endTime":"..."
+             (',"snapshotTime":"', S), ('","orchestrator":{"did":"', S), ('","type":"', S), ('","agentNodeDid":"', S),
+             ('"},"audit":{"inputDataHash":"', S), ('","outputDataHash":"', S), ('","metadata":', R)]
+    if with_proof:
+        parts += [('}},"proof":{"type":"', S), ('","created":"', S), ('","verificationMethod":"', S), ('","proofPurpose":"', S),
+                  ('","proofValue":"', S)]
+        tail = '"}}'
+    else:
+        tail = '}},"proof":' + go_json.vc_proof(go_json.EMPTY_PROOF) + "}"
+    return [p[0].encode() for p in parts] + [tail.encode()], [p[1] for p in parts]
+
+
+def workflow_vc_document_values(doc, proof=None):
+    """One workflow document's values in the order of workflow_vc_document_template."""
+    cs = doc["credentialSubject"]
+    orc, au = cs["orchestrator"], cs["audit"]
+    u = lambda s: s.encode("utf-8", "surrogatepass") if isinstance(s, str) else bytes(s)
+    vals = [go_json.string_list(doc["@context"]).encode(), go_json.string_list(doc["type"]).encode(), u(doc["id"]), u(doc["issuer"]),
+            u(doc["issuanceDate"]), u(cs["workflowId"]), u(cs["sessionId"]), go_json.string_list(cs["componentVcIds"]).encode("utf-8"),
+            b"%d" % int(cs["totalSteps"]), b"%d" % int(cs["completedSteps"]), u(cs["status"]), u(cs["startTime"]),
+            (b',"endTime":' + go_json.string(cs["endTime"]).encode("utf-8")) if cs.get("endTime") is not None else b"",
+            u(cs["snapshotTime"]), u(orc["did"]), u(orc["type"]), u(orc["agentNodeDid"]), u(au["inputDataHash"]), u(au["outputDataHash"]),
+            go_json.value(au.get("metadata")).encode("utf-8")]
     if proof is not None:
         vals += [u(proof.get("type", "")), u(proof.get("created", "")), u(proof.get("verificationMethod", "")),
                  u(proof.get("proofPurpose", "")), u(proof.get("proofValue", ""))]

@@ -98,6 +98,12 @@ class Context:
         _abi.check(self._lib.afc_keycache_info(self.handle, C.byref(mk), C.byref(ck), C.byref(md)), self.handle)
         return {"max_keys": mk.value, "cached_keys": ck.value, "last_mode": md.value}
 
+    def keycache_stats(self):
+        """How the last verify call was split (hot = through per-key tables, cold = generic kernel) and the running totals."""
+        st = _abi.KeycacheStats()
+        _abi.check(self._lib.afc_keycache_stats(self.handle, C.byref(st)), self.handle)
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
     def profile_begin(self, max_launches=4096):
         _abi.check(self._lib.afc_profile_begin(self.handle, max_launches), self.handle)
 

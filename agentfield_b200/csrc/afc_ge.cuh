@@ -408,6 +408,91 @@ AFC_HD int ge_key_row_bases(ge_p3* bases, const uint32_t* pk) {
     }
     return ok;
 }
+// ---- second construction of the per-key tables (round 2): what k_kc_chain / k_kc_rows run.
+// (1) The doubling chain is walked in stages of `nr` rows (so that the rows of stage s can be filled while the chain of stage
+//     s + 1 is still running) and leaves, per row i, three points in P3 form: P_i = 256^i (-A), 32 P_i and 64 P_i — the chain
+//     passes through them anyway (5 and 6 doublings after P_i), keeping them costs one multiplication each (their T).
+// (2) Row threads start their slice of 128 / KR_PARTS consecutive multiples from those helpers with at most two additions
+//     (instead of a private double-and-add of up to 6 doublings + 2 additions), run forward storing (X, Y, Z, prefix product of Z),
+//     take part in ONE field inversion per CTA (a product tree in shared memory, fe_invert_cta in k_ed25519.cu) and convert to
+//     affine on the way back: one inversion per NT threads instead of one per thread (265 of the 809 multiplications a
+//     32-entry slice used to cost).
+static constexpr int KB_PTS = 3;                 // points kept per row by the chain: P, 32 P, 64 P
+// Rows [r0, r0 + nr) of one key.  Stage 0 decodes the key; later stages continue from bases3[r0 * KB_PTS] (left there by the
+// previous stage).  Returns 1 if the key decodes (meaningful for r0 == 0 only); an undecodable key gets the neutral element so
+// that every later product stays well defined (its table is never used: lookups report ok = 0).
+template <class F = FeInline>
+AFC_HD int ge_key_chain_stage(ge_p3* bases3, const uint32_t* pk, int r0, int nr) {
+    ge_p3 P;
+    int ok = 1;
+    if (r0 == 0) {
+        ok = ge_frombytes<F>(P, pk);
+        fe_neg(P.X, P.X); fe_neg(P.T, P.T);
+        if (!ok) ge_p3_0(P);
+    } else {
+        P = bases3[r0 * KB_PTS];
+    }
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int i = r0; i < r0 + nr; i++) {
+        bases3[i * KB_PTS] = P;
+        const int last = i + 1 >= COMB_ROWS;
+#pragma unroll 1
+        for (int k = 0; k < (last ? 6 : 8); k++) {
+            ge_dbl<F>(t, P.X, P.Y, P.Z);
+            if (k == 4 || k == 5 || k == 7) {
+                ge_p1p1_to_p3<F>(P, t);
+                if (k == 4) bases3[i * KB_PTS + 1] = P;
+                if (k == 5) bases3[i * KB_PTS + 2] = P;
+            } else {
+                ge_p2 q; ge_p1p1_to_p2<F>(q, t); fe_copy(P.X, q.X); fe_copy(P.Y, q.Y); fe_copy(P.Z, q.Z);
+            }
+        }
+    }
+    if (r0 + nr < COMB_ROWS) bases3[(r0 + nr) * KB_PTS] = P;
+    return ok;
+}
+// Start point of slice `part` (of PARTS) of a row: M = (part * 128 / PARTS + 1) P from the row's helpers; c = P in cached form.
+template <class F, int PARTS>
+AFC_HD void ge_key_slice_start(ge_p3& M, ge_cached& c, const ge_p3* row3, int part) {
+    static_assert(PARTS == 1 || PARTS == 2 || PARTS == 4, "helpers cover 32 P and 64 P only");
+    ge_p3_to_cached<F>(c, row3[0]);
+    const int m = part * (COMB_COLS / PARTS);          // 0, 32, 64 or 96
+    ge_p1p1 t;
+    if (m == 0) { M = row3[0]; return; }
+    M = (m & 64) ? row3[2] : row3[1];
+    ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t);  // 64 P + P  or  32 P + P
+    if (m == 96) {
+        ge_cached c32; ge_p3_to_cached<F>(c32, row3[1]);
+        ge_addsub<F>(t, M, c32, 0); ge_p1p1_to_p3<F>(M, t);
+    }
+}
+// Forward half of ge_affine_run: X/Y/Z[j] = M + j P, Pz[j] = Z_0 ... Z_j; the caller inverts Pz[CH-1] (alone or shared).
+template <class F, int CH>
+AFC_HD void ge_affine_run_fwd(fe* X, fe* Y, fe* Z, fe* Pz, ge_p3& M, const ge_cached& c) {
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int j = 0; j < CH; j++) {
+        fe_copy(X[j], M.X); fe_copy(Y[j], M.Y); fe_copy(Z[j], M.Z);
+        if (j == 0) fe_copy(Pz[0], M.Z); else F::mul(Pz[j], Pz[j - 1], M.Z);
+        if (j + 1 < CH) { ge_addsub<F>(t, M, c, 0); ge_p1p1_to_p3<F>(M, t); }
+    }
+}
+// Backward half: inv = 1 / Pz[CH-1] on entry.
+template <class F, int CH>
+AFC_HD void ge_affine_run_bwd(ge_precomp* out, const fe* X, const fe* Y, const fe* Z, const fe* Pz, fe inv) {
+    fe d2; fe_const(d2, AFC_D2_32);
+#pragma unroll 1
+    for (int j = CH - 1; j >= 0; j--) {
+        fe zi;
+        if (j > 0) { F::mul(zi, inv, Pz[j - 1]); F::mul(inv, inv, Z[j]); } else fe_copy(zi, inv);
+        fe x, y, xy;
+        F::mul(x, X[j], zi); F::mul(y, Y[j], zi);
+        ge_precomp& r = out[j];
+        fe_add(r.ypx, y, x); fe_sub(r.ymx, y, x); F::mul(xy, x, y); F::mul(r.xy2d, xy, d2);
+    }
+}
+
 // Single-thread form (one row, its own doubling chain): what the first build of the cache did; kept as the independent check
 // of the two-step construction in tests/hostsim.
 template <class F = FeInline>

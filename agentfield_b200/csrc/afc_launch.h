@@ -10,21 +10,25 @@ namespace launch {
 
 // Launch accounting + optional per-kernel CUDA-event timing (afc_profile_*): when `profile` is set every kernel
 // launch is bracketed by two events on its own stream; afcrypto.cu aggregates them by kernel name after a sync.
-struct LaunchRec { const char* name; cudaEvent_t e0, e1; };
+struct LaunchRec { const char* name; cudaEvent_t e0, e1; bool done; };
 struct LaunchLog {
     unsigned long long n = 0;
     bool profile = false;
-    LaunchRec* recs = nullptr;       // capacity `cap`, filled up to `used`
-    int cap = 0, used = 0;
+    LaunchRec* pool = nullptr;       // the context's pool of event pairs; one is claimed per launch (never more than are used)
+    int cap = 0;
+    int* next = nullptr;             // shared claim counter (atomic on the host)
+    LaunchRec* cur = nullptr;
     cudaEvent_t begin(const char* name, cudaStream_t s) {
         ++n;
-        if (!profile || used >= cap) return nullptr;
-        LaunchRec& r = recs[used];
-        r.name = name;
-        cudaEventRecord(r.e0, s);
-        return r.e1;
+        if (!profile) return nullptr;
+        const int idx = __atomic_fetch_add(next, 1, __ATOMIC_RELAXED);
+        if (idx >= cap) return nullptr;
+        cur = &pool[idx];
+        cur->name = name; cur->done = false;
+        cudaEventRecord(cur->e0, s);
+        return cur->e1;
     }
-    void end(cudaEvent_t e1, cudaStream_t s) { if (e1) { cudaEventRecord(e1, s); ++used; } }
+    void end(cudaEvent_t e1, cudaStream_t s) { if (e1) { cudaEventRecord(e1, s); cur->done = true; } }
 };
 #define AFC_LAUNCH(lg, name, stream, ...)            \
     do {                                             \
@@ -67,24 +71,49 @@ cudaError_t microbench_hash(int which, uint32_t iters, uint32_t blocks, uint32_t
 size_t ed_tables_bytes();
 cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg);
 // Device buffers of the transparent issuer-key cache used by ed_verify_batch (see k_ed25519.cu); owned by afcrypto.cu.
+// state words (uint32 each)
+enum KcState {
+    KS_HIGH = 0,       // ids ever handed out (high-water mark, <= max_keys)
+    KS_NHOT = 1,       // credentials of the current call that go through tables
+    KS_NCOLD = 2,      // credentials of the current call left to the generic kernel
+    KS_DISTINCT = 3,   // distinct public keys in the current call
+    KS_NBUILD = 4,     // tables being built in the current call
+    KS_EPOCH = 5,      // call counter (LRU stamps)
+    KS_NCAND = 6,      // distinct keys of the call that are not cached and are used often enough to deserve a table
+    KS_NFREE = 7,      // entries of free_list
+    KS_REBUILD = 8,    // the persistent hash table must be rebuilt (something was evicted)
+    KS_EVICTED = 9,    // tables evicted in the current call
+    KS_TOTAL_BUILT = 10, KS_TOTAL_EVICTED = 11, KS_CALLS = 12,
+    KS_WORDS = 16
+};
 struct KeyCache {
-    uint32_t* slots;        // persistent open-addressing table: slot -> cache id, 0xffffffff = empty   (slot_mask + 1 entries)
+    // persistent
+    uint32_t* slots;        // open-addressing table: slot -> cache id, 0xffffffff = empty   (slot_mask + 1 entries)
     uint32_t slot_mask;
     uint32_t max_keys;
     uint8_t* cpks;          // max_keys x 32
-    uint8_t* valid;         // max_keys
+    uint8_t* valid;         // max_keys: key decodes
     void* tabs;             // max_keys x 32 x 128 ge_precomp
-    uint32_t* state;        // 8 words: [0] cached keys [1] mode [2] reset pending [3] distinct [4] to build [5] snapshot [6] missing
-    uint32_t* build_list;   // max_keys
-    void* bases;            // max_keys x 32 ge_p3: row base points of the tables being built in this call (indexed by build position)
-    uint32_t* bslots;       // per-call: batch de-duplication table (bmask + 1 entries, >= 2n)
+    uint32_t* stamp;        // max_keys: epoch of the last call that used the key, 0 = free id
+    uint32_t* free_list;    // max_keys: evicted ids waiting for reuse
+    uint32_t* bucket;       // max_keys + 1: credentials per id in the current call, then the scatter cursors
+    uint32_t* state;        // KS_WORDS
+    uint32_t* build_list;   // max_keys: ids whose tables are built in the current call
+    void* bases;            // max_keys x 32 x 3 ge_p3: chain output of the tables being built (indexed by build position)
+    // per call (capacity >= n)
+    uint32_t* bslots;       // batch de-duplication table (bmask + 1 entries, >= 2n)
     uint32_t bmask;
-    uint32_t* rep;          // per-call: n
-    uint32_t* kid;          // per-call: n
-    // the cache work of a call (de-duplication, table build) runs on `side`, a high-priority stream, between ev_fork and
-    // ev_join, while the caller's stream computes H(R||A||M), which does not depend on the cache
-    cudaStream_t side;
-    cudaEvent_t ev_fork, ev_join;
+    uint32_t* rep;          // credential -> representative credential (first with the same public key)
+    uint32_t* kid;          // representative -> cache id | KC_COLD
+    uint32_t* cnt;          // representative -> number of credentials with that key
+    uint32_t* dlist;        // distinct representatives
+    uint32_t* cand;         // representatives that want a table (at most n / KC_AMORTISE)
+    uint32_t* perm;         // hot credentials bucketed by cache id (KS_NHOT entries)
+    uint32_t* cold;         // cold credentials (KS_NCOLD entries)
+    // the cache work of a call runs on `side` (a high-priority stream) and `side2` between ev_fork and ev_join, while the
+    // caller's stream computes H(R||A||M), which does not depend on the cache
+    cudaStream_t side, side2;
+    cudaEvent_t ev_fork, ev_join, ev_plan, ev_rows, ev_chain[4];
 };
 cudaError_t ed_keycache_clear(const KeyCache& kc, cudaStream_t s, LaunchLog* lg);     // empties the persistent table (slots, counters)
 // scratch_k: n * 32 bytes; kc: nullable (nullptr = always the generic Straus kernel)

@@ -85,15 +85,14 @@ struct afc_ctx {
     // transparent issuer-key cache behind afc_ed25519_verify_batch (see k_ed25519.cu)
     launch::KeyCache kc{};
     bool kc_ready = false;
-    uint32_t kc_max_keys = 1024;        // AFC_KEYCACHE_MAX_KEYS / afc_keycache_configure; 0 disables
+    uint32_t kc_max_keys = 4096;        // AFC_KEYCACHE_MAX_KEYS / afc_keycache_configure; 0 disables (4096 keys = 1.6 GB of the 180 GB)
     uint32_t kc_call_cap = 0;           // per-call scratch capacity (items)
     std::mutex kc_mu;
     cudaEvent_t kc_event = nullptr;     // orders successive users of the cache across streams
     // per-kernel CUDA-event profiling (afc_profile_begin / afc_profile_end)
     bool profile = false;
     std::vector<launch::LaunchRec> prof_recs;
-    std::atomic<int> prof_next{0};
-    std::vector<std::pair<int, int>> prof_spans;    // (base, used) per call
+    int prof_next = 0;                  // claimed with __atomic_fetch_add (launch::LaunchLog::begin)
     // NCCL (lazy)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -145,33 +144,33 @@ void set_err(afc_ctx* ctx, cudaError_t e, const char* what) {
     ctx->last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
 }
 
-// Per-call launch log: counts launches, and when profiling is on claims a span of event pairs from the ctx pool.
+// Per-call launch log: counts launches; when profiling is on every launch claims one event pair from the ctx pool.
 struct CallLog {
     afc_ctx* ctx;
     launch::LaunchLog lg;
-    int base = 0;
-    explicit CallLog(afc_ctx* c, int want = 96) : ctx(c) {
-        if (ctx->profile) {
-            base = ctx->prof_next.fetch_add(want);
-            if (base + want <= (int)ctx->prof_recs.size()) { lg.profile = true; lg.recs = ctx->prof_recs.data() + base; lg.cap = want; }
-        }
+    explicit CallLog(afc_ctx* c, int = 0) : ctx(c) {
+        if (ctx->profile) { lg.profile = true; lg.pool = ctx->prof_recs.data(); lg.cap = (int)ctx->prof_recs.size(); lg.next = &ctx->prof_next; }
     }
-    ~CallLog() {
-        ctx->launches += lg.n;
-        if (lg.profile && lg.used) { std::lock_guard<std::mutex> g(ctx->mu); ctx->prof_spans.emplace_back(base, lg.used); }
-    }
+    ~CallLog() { ctx->launches += lg.n; }
     operator launch::LaunchLog*() { return &lg; }
 };
 
 
 // ---- issuer-key cache management ------------------------------------------------------------------------------
+void kc_free_call_buffers(launch::KeyCache& k) {
+    void* ps[] = {k.bslots, k.rep, k.kid, k.cnt, k.dlist, k.cand, k.perm, k.cold};
+    for (void* p : ps) if (p) cudaFree(p);
+    k.bslots = k.rep = k.kid = k.cnt = k.dlist = k.cand = k.perm = k.cold = nullptr;
+}
 void kc_free(afc_ctx* ctx) {
     launch::KeyCache& k = ctx->kc;
-    void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.state, k.build_list, k.bases, k.bslots, k.rep, k.kid};
+    void* ps[] = {k.slots, k.cpks, k.valid, k.tabs, k.stamp, k.free_list, k.bucket, k.state, k.build_list, k.bases};
     for (void* p : ps) if (p) cudaFree(p);
+    kc_free_call_buffers(k);
     if (k.side) cudaStreamDestroy(k.side);
-    if (k.ev_fork) cudaEventDestroy(k.ev_fork);
-    if (k.ev_join) cudaEventDestroy(k.ev_join);
+    if (k.side2) cudaStreamDestroy(k.side2);
+    cudaEvent_t evs[] = {k.ev_fork, k.ev_join, k.ev_plan, k.ev_rows, k.ev_chain[0], k.ev_chain[1], k.ev_chain[2], k.ev_chain[3]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     k = launch::KeyCache{};
     ctx->kc_ready = false; ctx->kc_call_cap = 0;
 }
@@ -180,35 +179,38 @@ void kc_free(afc_ctx* ctx) {
 const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
     if (ctx->kc_max_keys == 0 || n < 64) return nullptr;
     launch::KeyCache& k = ctx->kc;
+    auto dmalloc = [](auto** p, size_t bytes) { return cudaMalloc((void**)p, bytes ? bytes : 1) == cudaSuccess; };
     if (!ctx->kc_ready) {
-        uint32_t cap = 1; while (cap < 4 * ctx->kc_max_keys) cap <<= 1;
+        uint32_t cap = 1; while (cap < 4 * (uint64_t)ctx->kc_max_keys) cap <<= 1;
         k.slot_mask = cap - 1; k.max_keys = ctx->kc_max_keys;
+        const size_t mk = k.max_keys;
         int prio_least = 0, prio_greatest = 0;
-        bool ok = cudaMalloc((void**)&k.slots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.cpks, (size_t)k.max_keys * 32) == cudaSuccess &&
-                  cudaMalloc((void**)&k.valid, k.max_keys) == cudaSuccess && cudaMalloc(&k.tabs, launch::ed_key_table_bytes(k.max_keys)) == cudaSuccess &&
-                  cudaMalloc((void**)&k.state, 8 * 4) == cudaSuccess && cudaMalloc((void**)&k.build_list, (size_t)k.max_keys * 4) == cudaSuccess &&
-                  cudaMalloc(&k.bases, launch::ed_key_bases_bytes(k.max_keys)) == cudaSuccess &&
-                  cudaMemset(k.slots, 0xff, (size_t)cap * 4) == cudaSuccess && cudaMemset(k.state, 0, 8 * 4) == cudaSuccess &&
-                  cudaMemset(k.valid, 0, k.max_keys) == cudaSuccess &&
+        bool ok = dmalloc(&k.slots, (size_t)cap * 4) && dmalloc(&k.cpks, mk * 32) && dmalloc(&k.valid, mk) &&
+                  dmalloc(&k.tabs, launch::ed_key_table_bytes(k.max_keys)) && dmalloc(&k.stamp, mk * 4) && dmalloc(&k.free_list, mk * 4) &&
+                  dmalloc(&k.bucket, (mk + 1) * 4) && dmalloc(&k.state, launch::KS_WORDS * 4) && dmalloc(&k.build_list, mk * 4) &&
+                  dmalloc(&k.bases, launch::ed_key_bases_bytes(k.max_keys)) &&
+                  cudaMemset(k.slots, 0xff, (size_t)cap * 4) == cudaSuccess && cudaMemset(k.state, 0, launch::KS_WORDS * 4) == cudaSuccess &&
+                  cudaMemset(k.valid, 0, mk) == cudaSuccess && cudaMemset(k.stamp, 0, mk * 4) == cudaSuccess &&
                   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess &&
                   cudaStreamCreateWithPriority(&k.side, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&k.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&k.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&k.side2, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
                   (ctx->kc_event || cudaEventCreateWithFlags(&ctx->kc_event, cudaEventDisableTiming) == cudaSuccess);
+        cudaEvent_t* evs[] = {&k.ev_fork, &k.ev_join, &k.ev_plan, &k.ev_rows, &k.ev_chain[0], &k.ev_chain[1], &k.ev_chain[2], &k.ev_chain[3]};
+        for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { cudaGetLastError(); kc_free(ctx); ctx->kc_max_keys = 0; return nullptr; }     // no room: stay generic
         ctx->kc_ready = true;
     }
     if (n > ctx->kc_call_cap) {
-        if (k.bslots) cudaFree(k.bslots);
-        if (k.rep) cudaFree(k.rep);
-        if (k.kid) cudaFree(k.kid);
-        k.bslots = k.rep = k.kid = nullptr;
-        uint32_t want = n + n / 4;
-        uint32_t cap = 1; while (cap < 2 * (uint64_t)want && cap < 0x80000000u) cap <<= 1;
-        bool ok = cudaMalloc((void**)&k.bslots, (size_t)cap * 4) == cudaSuccess && cudaMalloc((void**)&k.rep, (size_t)want * 4) == cudaSuccess &&
-                  cudaMalloc((void**)&k.kid, (size_t)want * 4) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); ctx->kc_call_cap = 0; return nullptr; }
-        k.bmask = cap - 1; ctx->kc_call_cap = want;
+        // earlier calls may still be using the per-call buffers on their streams: wait for the last cache user before freeing
+        if (ctx->kc_call_cap) { cudaEventSynchronize(ctx->kc_event); }
+        kc_free_call_buffers(k);
+        const uint64_t want = (uint64_t)n + n / 4;
+        uint64_t cap = 1; while (cap < 2 * want) cap <<= 1;
+        if (cap > 0x80000000ull) { ctx->kc_call_cap = 0; return nullptr; }                    // beyond the 32-bit tables: generic kernel
+        bool ok = dmalloc(&k.bslots, (size_t)cap * 4) && dmalloc(&k.rep, want * 4) && dmalloc(&k.kid, want * 4) && dmalloc(&k.cnt, want * 4) &&
+                  dmalloc(&k.dlist, want * 4) && dmalloc(&k.cand, want * 4) && dmalloc(&k.perm, want * 4) && dmalloc(&k.cold, want * 4);
+        if (!ok) { cudaGetLastError(); kc_free_call_buffers(k); ctx->kc_call_cap = 0; return nullptr; }
+        k.bmask = (uint32_t)(cap - 1); ctx->kc_call_cap = (uint32_t)(want > 0xffffffffull ? 0xffffffffu : want);
     }
     return &k;
 }
@@ -438,9 +440,12 @@ int afc_init(int device, afc_ctx** out) {
         for (int s = 0; s < kSlots; s++)
             if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&ctx->comb, launch::ed_tables_bytes())) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
-    CallLog lc(ctx);
     cudaStream_t s0 = ctx->lanes[0].slot[0].stream;
-    if ((e = launch::ed_build_tables(ctx->comb, s0, lc)) != cudaSuccess) return fail(e, "ed_build_tables");
+    {   // the launch log must be gone before fail() can destroy the context it points into
+        CallLog lc(ctx);
+        e = launch::ed_build_tables(ctx->comb, s0, lc);
+    }
+    if (e != cudaSuccess) return fail(e, "ed_build_tables");
     if ((e = cudaStreamSynchronize(s0)) != cudaSuccess) return fail(e, "ed_build_tables sync");
     *out = ctx;
     return AFC_OK;
@@ -670,15 +675,34 @@ int afc_keycache_clear(afc_ctx* ctx, void* stream) {
     CK(cudaEventRecord(ctx->kc_event, st));
     return AFC_OK;
 }
+static int kc_read_state(afc_ctx* ctx, uint32_t* st) {
+    memset(st, 0, launch::KS_WORDS * 4);
+    if (ctx->kc_ready) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(st, ctx->kc.state, launch::KS_WORDS * 4, cudaMemcpyDeviceToHost)); }
+    return AFC_OK;
+}
 int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode) {
     if (!ctx) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->kc_mu);
-    uint32_t st[8] = {0};
-    if (ctx->kc_ready) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(st, ctx->kc.state, sizeof st, cudaMemcpyDeviceToHost)); }
+    uint32_t st[launch::KS_WORDS];
+    int rc = kc_read_state(ctx, st);
+    if (rc != AFC_OK) return rc;
     if (max_keys) *max_keys = ctx->kc_max_keys;
-    if (cached_keys) *cached_keys = st[0];
-    if (last_mode) *last_mode = st[1];
+    if (cached_keys) *cached_keys = st[launch::KS_HIGH] - st[launch::KS_NFREE];
+    if (last_mode) *last_mode = st[launch::KS_NHOT] ? 1u : 0u;
+    return AFC_OK;
+}
+int afc_keycache_stats(afc_ctx* ctx, afc_keycache_stats_t* out) {
+    if (!ctx || !out) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->kc_mu);
+    uint32_t st[launch::KS_WORDS];
+    int rc = kc_read_state(ctx, st);
+    if (rc != AFC_OK) return rc;
+    out->max_keys = ctx->kc_max_keys; out->cached_keys = st[launch::KS_HIGH] - st[launch::KS_NFREE];
+    out->last_hot = st[launch::KS_NHOT]; out->last_cold = st[launch::KS_NCOLD]; out->last_distinct = st[launch::KS_DISTINCT];
+    out->last_built = st[launch::KS_NBUILD]; out->last_evicted = st[launch::KS_EVICTED];
+    out->total_built = st[launch::KS_TOTAL_BUILT]; out->total_evicted = st[launch::KS_TOTAL_EVICTED]; out->calls = st[launch::KS_CALLS];
     return AFC_OK;
 }
 
@@ -1172,15 +1196,17 @@ int afc_profile_begin(afc_ctx* ctx, int max_launches) {
     if ((size_t)max_launches > old) {
         ctx->prof_recs.resize(max_launches);
         for (size_t i = old; i < ctx->prof_recs.size(); i++) {
-            ctx->prof_recs[i].name = nullptr;
+            ctx->prof_recs[i].name = nullptr; ctx->prof_recs[i].done = false;
             if (cudaEventCreate(&ctx->prof_recs[i].e0) != cudaSuccess || cudaEventCreate(&ctx->prof_recs[i].e1) != cudaSuccess) return AFC_ECUDA;
         }
     }
-    ctx->prof_next = 0;
-    ctx->prof_spans.clear();
+    for (auto& r : ctx->prof_recs) r.done = false;
+    __atomic_store_n(&ctx->prof_next, 0, __ATOMIC_RELAXED);
     ctx->profile = true;
     return AFC_OK;
 }
+// Returns the number of distinct kernel names (entries written to out, at most cap).  Launches beyond the pool given to
+// afc_profile_begin were not timed: they are reported in the entry named "(untimed)" (count only) so that a short pool is visible.
 int afc_profile_end(afc_ctx* ctx, afc_profile_entry* out, int cap) {
     if (!ctx || (cap > 0 && !out)) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -1189,27 +1215,33 @@ int afc_profile_end(afc_ctx* ctx, afc_profile_entry* out, int cap) {
     if (!ctx->profile) return AFC_ESTATE;
     ctx->profile = false;
     int n_out = 0;
-    for (auto& sp : ctx->prof_spans) {
-        for (int i = 0; i < sp.second; i++) {
-            launch::LaunchRec& r = ctx->prof_recs[sp.first + i];
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
-            int k = 0;
-            for (; k < n_out; k++) if (strncmp(out[k].name, r.name, sizeof(out[k].name) - 1) == 0) break;
-            if (k == n_out) {
-                if (n_out >= cap) continue;
-                memset(&out[k], 0, sizeof(out[k]));
-                strncpy(out[k].name, r.name, sizeof(out[k].name) - 1);
-                out[k].min_ms = ms; out[k].max_ms = ms;
-                n_out++;
-            }
-            out[k].count++;
-            out[k].total_ms += ms;
-            if (ms < out[k].min_ms) out[k].min_ms = ms;
-            if (ms > out[k].max_ms) out[k].max_ms = ms;
+    const int claimed = __atomic_load_n(&ctx->prof_next, __ATOMIC_RELAXED);
+    const int timed = claimed < (int)ctx->prof_recs.size() ? claimed : (int)ctx->prof_recs.size();
+    for (int i = 0; i < timed; i++) {
+        launch::LaunchRec& r = ctx->prof_recs[i];
+        if (!r.done) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        int k = 0;
+        for (; k < n_out; k++) if (strncmp(out[k].name, r.name, sizeof(out[k].name) - 1) == 0) break;
+        if (k == n_out) {
+            if (n_out >= cap) continue;
+            memset(&out[k], 0, sizeof(out[k]));
+            strncpy(out[k].name, r.name, sizeof(out[k].name) - 1);
+            out[k].min_ms = ms; out[k].max_ms = ms;
+            n_out++;
         }
+        out[k].count++;
+        out[k].total_ms += ms;
+        if (ms < out[k].min_ms) out[k].min_ms = ms;
+        if (ms > out[k].max_ms) out[k].max_ms = ms;
     }
-    ctx->prof_spans.clear();
+    if (claimed > timed && n_out < cap) {
+        memset(&out[n_out], 0, sizeof(out[n_out]));
+        strncpy(out[n_out].name, "(untimed)", sizeof(out[n_out].name) - 1);
+        out[n_out].count = (uint32_t)(claimed - timed);
+        n_out++;
+    }
     return n_out;
 }
 

@@ -58,8 +58,11 @@ k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, con
 template <class F, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs,
-            const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok, const uint32_t* __restrict__ skip_if_set) {
-    if (skip_if_set && *skip_if_set) return;    // the table-driven kernel handled this batch (uniform across the grid)
+            const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok, const uint32_t* __restrict__ list,
+            const uint32_t* __restrict__ n_list) {
+    // with a list: only the credentials the issuer-key cache left to this kernel (the launch is sized for all n; CTAs past the
+    // end of the list leave at once)
+    if (list) { n = *n_list; if (blockIdx.x * blockDim.x >= n) return; }
     __shared__ ge_precomp sB[COMB_COLS];         // (j+1)B, j = 0..127: 12 KB, staged with 128-bit loads
     {
         const uint4* src = (const uint4*)comb;
@@ -69,6 +72,7 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
     __syncthreads();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (list) i = list[i];
     uint32_t pk[8], sig[16], k[8];
     load_words8(pk, pks + 32ull * i);
     load_words8(sig, sigs + 64ull * i);
@@ -77,7 +81,7 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
     ok[i] = (uint8_t)ed25519_verify_core<F>(pk, sig, k, sB);
 }
 
-// ---- keyed verification (identity cache): per-key radix-256 tables of -A, built once per key set
+// ---- table-driven verification: per-key radix-256 tables of -A (identity cache N1 and the transparent issuer-key cache)
 // Credentials per thread in the table-driven kernels (they share ONE field inversion, Montgomery's trick).  The group size is a
 // launch parameter: every thread does the same work, so a launch runs in whole waves of `resident threads`; pick_group() chooses
 // G in [1, KC_GMAX] so that the last wave is full and the inversion share small (1 M credentials on 148 SMs x 512 threads: G = 7,
@@ -87,10 +91,13 @@ constexpr int KC_GMAX = 8;
 #define AFC_CACHED_MINB 3      // 5 (96 registers, 20 warps/SM) was measured: 4.5 ms, spills
 #endif
 
-// Shared body: thread t of T handles credentials t, t + T, t + 2T, ... (G of them; lanes stay adjacent in memory).
-// lookup(i, atab) -> false when credential i's key is unknown or does not decode (ok = 0, arithmetic skipped).
-template <class Lookup>
-__device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
+// Shared body: thread t of T handles positions t, t + T, t + 2T, ... of an ORDER of the credentials (G of them; lanes stay
+// adjacent in that order).  item(p) -> credential index of position p: the identity for the key-set kernel without a
+// permutation, or the issuer-bucketed permutation — consecutive positions then share their issuer, so the 32 lanes of a warp
+// gather from ONE 12 KB table row per step instead of 32 different 384 KB tables (round 1: 6.97 GB of DRAM traffic per 1 M
+// credentials, L2 hit rate 45 %).  lookup(i, atab) -> false when credential i's key is unknown or does not decode (ok = 0).
+template <class Item, class Lookup>
+__device__ __forceinline__ void table_verify_group(Item item, Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
                                                    const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
@@ -98,11 +105,12 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
     uint32_t good = 0;
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
-        uint64_t i = (uint64_t)t + (uint64_t)g * T;
+        uint64_t p = (uint64_t)t + (uint64_t)g * T;
         fe_0(X[g]); fe_1(Y[g]); fe_1(Z[g]);
-        if (i >= n) continue;
+        if (p >= n) continue;
+        const uint32_t i = item((uint32_t)p);
         const ge_precomp* atab;
-        if (!lookup((uint32_t)i, atab)) continue;
+        if (!lookup(i, atab)) continue;
         uint32_t sig[16], k[8];
         load_words8(sig, sigs + 64ull * i);
         load_words8(sig + 8, sigs + 64ull * i + 32);
@@ -115,8 +123,9 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
     ge_encode_group<FeInline, KC_GMAX>(enc, X, Y, Z, G);
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
-        uint64_t i = (uint64_t)t + (uint64_t)g * T;
-        if (i >= n) break;
+        uint64_t p = (uint64_t)t + (uint64_t)g * T;
+        if (p >= n) break;
+        const uint32_t i = item((uint32_t)p);
         uint32_t r[8];
         load_words8(r, sigs + 64ull * i);
         uint32_t diff = 0;
@@ -125,32 +134,157 @@ __device__ __forceinline__ void table_verify_group(Lookup lookup, const ge_preco
         ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
     }
 }
-// Per-key tables are built in two steps: one thread per key walks the doubling chain and leaves the 32 row base points
-// 256^i (-A) in scratch (latency-bound, a handful of warps: it hides behind whatever else is running), then one thread per row
-// turns its base point into 128 affine entries — uniform work, no doublings.  (One thread per row doing its own 8 i doublings:
-// 2.05 ms per 1024 keys, lanes of a warp idle for up to 248 doublings.)
+
+// ---- building per-key tables --------------------------------------------------------------------------------------------
+// Two kernels per stage of rows (ge_key_chain_stage / ge_key_slice_start + ge_affine_run_fwd/bwd in afc_ge.cuh):
+//   k_kc_chain  one thread per key walks the doubling chain through the stage's rows (latency-bound: a handful of warps)
+//   k_kc_rows   one thread per slice of 128 / KR_PARTS table entries; ONE field inversion per CTA
+// `list` maps build position -> table id (nullptr: identity), `count` the number of keys (device value if count_dev).
 #ifndef AFC_BASES_FE
 #define AFC_BASES_FE FeInline      // the chain is latency-bound (one warp per 32 keys): inlined multiplies let the 4 squarings of a doubling overlap
 #endif
-__global__ void __launch_bounds__(32)
-k_ed_key_bases(const uint8_t* __restrict__ pks, uint32_t n_keys, ge_p3* __restrict__ bases, uint8_t* __restrict__ valid) {
-    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= n_keys) return;
-    uint32_t pk[8];
-    load_words8(pk, pks + 32ull * key);
-    valid[key] = (uint8_t)ge_key_row_bases<AFC_BASES_FE>(bases + (size_t)key * COMB_ROWS, pk);
-}
 #ifndef AFC_KEYROW_PARTS
-#define AFC_KEYROW_PARTS 4          // threads per table row in the second step (128 / PARTS entries and one inversion each)
+#define AFC_KEYROW_PARTS 4          // threads per table row (128 / PARTS entries each)
 #endif
-constexpr int KR_PARTS = AFC_KEYROW_PARTS, KR_SLICE = COMB_COLS / KR_PARTS;
+#ifndef AFC_ROWS_THREADS
+#define AFC_ROWS_THREADS 256        // CTA size of k_kc_rows = slices that share one field inversion
+#endif
+#ifndef AFC_ROWS_MINB
+#define AFC_ROWS_MINB 2             // CTAs per SM the register budget of k_kc_rows is capped for (2 x 256 threads: <= 128 registers)
+#endif
+constexpr int KR_PARTS = AFC_KEYROW_PARTS, KR_SLICE = COMB_COLS / KR_PARTS, KR_NT = AFC_ROWS_THREADS;
+
+struct KeyBuild {
+    const uint8_t* pks;          // 32-byte keys, indexed by table id
+    const uint32_t* list;        // build position -> table id, or nullptr (identity)
+    const uint32_t* count_dev;   // number of keys to build (device), or nullptr
+    uint32_t count;              // number of keys to build when count_dev is nullptr; otherwise the launch bound
+    ge_p3* bases3;               // count x COMB_ROWS x KB_PTS (indexed by build position)
+    ge_precomp* tabs;            // indexed by table id
+    uint8_t* valid;              // indexed by table id
+};
+__device__ __forceinline__ uint32_t kb_count(const KeyBuild& b) { return b.count_dev ? min(*b.count_dev, b.count) : b.count; }
+
 __global__ void __launch_bounds__(32)
-k_ed_key_rows(uint32_t n_keys, const ge_p3* __restrict__ bases, ge_precomp* __restrict__ tabs) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_keys * COMB_ROWS * KR_PARTS) return;
-    uint32_t r = t / KR_PARTS, part = t % KR_PARTS;
-    ge_p3 P = bases[r];
-    ge_key_row_slice<FeCall, KR_SLICE>(tabs + (size_t)r * COMB_COLS, P, (int)part * KR_SLICE);
+k_kc_chain(KeyBuild b, int r0, int nr) {
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= kb_count(b)) return;
+    const uint32_t id = b.list ? b.list[pos] : pos;
+    uint32_t pk[8];
+    load_words8(pk, b.pks + 32ull * id);
+    const int ok = ge_key_chain_stage<AFC_BASES_FE>(b.bases3 + (size_t)pos * COMB_ROWS * KB_PTS, pk, r0, nr);
+    if (r0 == 0) b.valid[id] = (uint8_t)ok;
+}
+
+// The same chain with FOUR lanes per key (Hisil-Wong-Carter-Dawson: the four squarings of a doubling are independent, and so
+// are the four products that complete it).  Lane `role` of a quad owns one coordinate (0 X, 1 Y, 2 Z, 3 T): per doubling every
+// lane does ONE squaring and ONE multiplication instead of four and three-to-four, and the quad exchanges 48 words by shuffle.
+// The chain is pure latency (248 dependent doublings per key, a handful of warps on the whole GPU): 2.6x fewer instructions
+// per warp is 2.6x less of it.  T comes for free (lane 3), so every point the rows need is already in P3 form.
+__device__ __forceinline__ void fe_shfl(fe& r, const fe& v, int src) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) r.v[w] = __shfl_sync(0xffffffffu, v.v[w], src);
+}
+__device__ __forceinline__ void quad_double(fe& C, int role, int q0) {
+    fe xs, ys, in, t;
+    fe_shfl(xs, C, q0); fe_shfl(ys, C, q0 + 1);
+    fe_add(t, xs, ys);
+    fe_select(in, C, t, role == 3);                    // X, Y, Z, X + Y
+    fe_sq(in, in);
+    fe_dbl(t, in);
+    fe_select(in, in, t, role == 2);                   // X^2, Y^2, 2 Z^2, (X + Y)^2
+    fe xx, yy, bb, aa;
+    fe_shfl(xx, in, q0); fe_shfl(yy, in, q0 + 1); fe_shfl(bb, in, q0 + 2); fe_shfl(aa, in, q0 + 3);
+    fe rX, rY, rZ, rT, u, v;
+    fe_add(rY, yy, xx); fe_sub(rZ, yy, xx); fe_sub(rX, aa, rY); fe_sub(rT, bb, rZ);
+    fe_select(u, rX, rY, role == 1); fe_select(u, u, rZ, role == 2);            // rX rY rZ rX
+    fe_select(v, rT, rZ, role == 1); fe_select(v, v, rY, role == 3);            // rT rZ rT rY
+    fe_mul(C, u, v);                                   // X3 = rX rT, Y3 = rY rZ, Z3 = rZ rT, T3 = rX rY
+}
+__global__ void __launch_bounds__(32)
+k_kc_chain4(KeyBuild b) {
+    const int lane = threadIdx.x & 31, role = lane & 3, q0 = lane & ~3;
+    const uint32_t pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (blockIdx.x * (blockDim.x >> 2) >= kb_count(b)) return;             // whole warp out of range
+    const bool live = pos < kb_count(b);
+    const uint32_t id = live ? (b.list ? b.list[pos] : pos) : 0;
+    uint32_t pk[8] = {1, 0, 0, 0, 0, 0, 0, 0};                             // idle quads walk the neutral element
+    if (live) load_words8(pk, b.pks + 32ull * id);
+    ge_p3 P;
+    const int ok = ge_frombytes<AFC_BASES_FE>(P, pk);
+    fe_neg(P.X, P.X); fe_neg(P.T, P.T);
+    if (!ok) ge_p3_0(P);
+    if (live && role == 0) b.valid[id] = (uint8_t)ok;
+    fe C;
+    fe_select(C, P.X, P.Y, role == 1); fe_select(C, C, P.Z, role == 2); fe_select(C, C, P.T, role == 3);
+    fe* out = (fe*)(b.bases3 + (size_t)pos * COMB_ROWS * KB_PTS);          // ge_p3 = {X, Y, Z, T}: lane `role` writes field `role`
+#pragma unroll 1
+    for (int i = 0; i < COMB_ROWS; i++) {
+        if (live) out[(i * KB_PTS + 0) * 4 + role] = C;
+        const int nd = i + 1 < COMB_ROWS ? 8 : 6;
+#pragma unroll 1
+        for (int k = 0; k < nd; k++) {
+            quad_double(C, role, q0);
+            if (live && k == 4) out[(i * KB_PTS + 1) * 4 + role] = C;
+            if (live && k == 5) out[(i * KB_PTS + 2) * 4 + role] = C;
+        }
+    }
+}
+
+// 1 / q for every thread of the CTA with ONE field inversion: product tree in shared memory (tree[2 NT]), the root inverted by
+// thread 0, inverses pushed back down (inv(left) = inv(parent) x right, inv(right) = inv(parent) x left).  Every q must be
+// non-zero (Z coordinates of curve points: the addition law is complete; undecodable keys were replaced by the neutral element).
+template <class F, int NT>
+__device__ __forceinline__ void fe_invert_cta(fe& inv, const fe& q, fe* tree) {
+    const int tid = threadIdx.x;
+    tree[tid] = q;
+    int off = 0, cnt = NT;
+    while (cnt > 1) {
+        __syncthreads();
+        const int half = cnt >> 1;
+        if (tid < half) { fe r; F::mul(r, tree[off + 2 * tid], tree[off + 2 * tid + 1]); tree[off + cnt + tid] = r; }
+        off += cnt; cnt = half;
+    }
+    __syncthreads();
+    if (tid == 0) { fe r; fe_invert<F>(r, tree[off]); tree[off] = r; }
+    while (cnt < NT) {
+        __syncthreads();
+        const int cnt2 = cnt << 1, off2 = off - cnt2;
+        if (tid < cnt) {
+            fe iv = tree[off + tid], L = tree[off2 + 2 * tid], R = tree[off2 + 2 * tid + 1], a, c;
+            F::mul(a, iv, R); F::mul(c, iv, L);
+            tree[off2 + 2 * tid] = a; tree[off2 + 2 * tid + 1] = c;
+        }
+        off = off2; cnt = cnt2;
+    }
+    __syncthreads();
+    inv = tree[tid];
+}
+
+__global__ void __launch_bounds__(KR_NT, AFC_ROWS_MINB)
+k_kc_rows(KeyBuild b, int r0, int nr) {
+    __shared__ fe tree[2 * KR_NT];
+    const uint32_t per_key = (uint32_t)nr * KR_PARTS;
+    const uint64_t total = (uint64_t)kb_count(b) * per_key;
+    if ((uint64_t)blockIdx.x * KR_NT >= total) return;                     // whole CTA out of range (uniform)
+    const uint64_t g = (uint64_t)blockIdx.x * KR_NT + threadIdx.x;
+    const bool live = g < total;
+    fe X[KR_SLICE], Y[KR_SLICE], Z[KR_SLICE], Pz[KR_SLICE];
+    fe q; fe_1(q);
+    ge_precomp* out = nullptr;
+    if (live) {
+        const uint32_t pos = (uint32_t)(g / per_key), within = (uint32_t)(g % per_key);
+        const int row = r0 + (int)(within / KR_PARTS), part = (int)(within % KR_PARTS);
+        const uint32_t id = b.list ? b.list[pos] : pos;
+        ge_p3 M; ge_cached c;
+        ge_key_slice_start<FeCall, KR_PARTS>(M, c, b.bases3 + ((size_t)pos * COMB_ROWS + row) * KB_PTS, part);
+        ge_affine_run_fwd<FeCall, KR_SLICE>(X, Y, Z, Pz, M, c);
+        fe_copy(q, Pz[KR_SLICE - 1]);
+        out = b.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS + part * KR_SLICE;
+    }
+    fe inv;
+    fe_invert_cta<FeCall, KR_NT>(inv, q, tree);
+    if (live) ge_affine_run_bwd<FeCall, KR_SLICE>(out, X, Y, Z, Pz, inv);
 }
 
 __global__ void __launch_bounds__(ED_THREADS)
@@ -173,7 +307,7 @@ __global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                   const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
                   const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
-    table_verify_group([&](uint32_t i, const ge_precomp*& atab) {
+    table_verify_group([](uint32_t p) { return p; }, [&](uint32_t i, const ge_precomp*& atab) {
         uint32_t key = key_index[i];
         if (key >= n_keys || !valid[key]) return false;      // unknown index or undecodable key: ok = 0
         atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
@@ -183,14 +317,23 @@ k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restr
 
 // ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
 // Issuers repeat: the reference verifies against the DIDs its own registry derived (vc_service.go:259), BASELINE's
-// configs[1] draws 10^6 credentials from 1024 keys.  The generic entry point therefore (1) de-duplicates the batch's public
-// keys in a device hash table, (2) looks the distinct keys up in a persistent per-context cache of radix-256 tables,
-// (3) decides ON THE DEVICE whether amortised table building pays (new keys x ~48 verify-equivalents <= batch size and the
-// cache has room), builds the missing tables and (4) runs either the table-driven kernel or the generic Straus kernel —
-// the other one exits immediately.  No host synchronisation; results are bit-identical either way.
+// configs[1] draws 10^6 credentials from 1024 keys.  The generic entry point therefore, on the device and without a host
+// synchronisation:
+//   (1) de-duplicates the batch's public keys in a hash table and counts the credentials of each        k_kc_dedup
+//   (2) looks the distinct keys up in a persistent per-context cache of radix-256 tables                 k_kc_dedup
+//   (3) decides PER KEY: cached -> hot; not cached but used >= KC_AMORTISE times in this batch -> gets a table (evicting the
+//       least recently used tables if the cache is full) -> hot; everything else -> cold                k_kc_plan1 / k_kc_plan2
+//   (4) builds the missing tables                                                                        k_kc_chain / k_kc_rows
+//   (5) buckets the hot credentials by table id, lists the cold ones                                    k_kc_scan / k_kc_scatter
+//   (6) runs the table-driven kernel over the hot order and the generic Straus kernel over the cold list — in the same call.
+// Results are bit-identical whichever way a credential goes (same group element, same canonical comparison).
 using KeyCacheDev = launch::KeyCache;     // POD descriptor of the device buffers (afc_launch.h)
-constexpr uint32_t KC_EMPTY = 0xffffffffu;
-constexpr uint32_t KC_AMORTISE = 48;      // one table costs about this many generic verifications
+using namespace launch;                   // KS_* state indices
+constexpr uint32_t KC_EMPTY = 0xffffffffu, KC_COLD = 0xfffffffeu;
+#ifndef AFC_KC_AMORTISE
+#define AFC_KC_AMORTISE 48
+#endif
+constexpr uint32_t KC_AMORTISE = AFC_KC_AMORTISE;      // a table costs about this many generic verifications
 
 __device__ __forceinline__ uint32_t kc_hash(const uint32_t* w) {
     uint32_t h = w[0] * 0x9E3779B1u ^ w[1];
@@ -206,6 +349,17 @@ __device__ __forceinline__ bool kc_equal(const uint32_t* a, const uint8_t* p) {
     for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
     return d == 0;
 }
+// One atomicAdd per distinct target among the lanes of a warp that call this together: the leader of each group of lanes
+// with the same address adds the group's size and every lane gets its own slot (credentials of one issuer often arrive
+// together, and the cold list has a single counter).
+__device__ __forceinline__ uint32_t kc_grouped_add(uint32_t* addr) {
+    const uint32_t mask = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)addr);
+    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(addr, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1));
+}
 
 // Plain fills as kernels of our own: cudaMemsetAsync in these streams was measured to cost anything from microseconds to
 // ~0.7 ms per call depending on what else the driver had in flight (a 16-byte memset per staged chunk: +3.5 ms per host call).
@@ -215,13 +369,18 @@ k_fill_u32(uint32_t* __restrict__ p, uint32_t v, uint64_t n) {
     if (i + 3 < n) { *(uint4*)(p + i) = make_uint4(v, v, v, v); return; }
     for (; i < n; i++) p[i] = v;
 }
-__global__ void k_kc_begin(KeyCacheDev kc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        kc.state[1] = 0; kc.state[3] = 0; kc.state[4] = 0; kc.state[6] = 0;
-        kc.state[5] = kc.state[0];
+// start of a call: per-call counters, next epoch, per-id credential counts zeroed
+__global__ void __launch_bounds__(256)
+k_kc_begin(KeyCacheDev kc) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = t; i <= kc.max_keys; i += gridDim.x * blockDim.x) kc.bucket[i] = 0;
+    if (t == 0) {
+        kc.state[KS_NHOT] = 0; kc.state[KS_NCOLD] = 0; kc.state[KS_DISTINCT] = 0; kc.state[KS_NBUILD] = 0; kc.state[KS_NCAND] = 0;
+        kc.state[KS_REBUILD] = 0; kc.state[KS_EVICTED] = 0;
+        kc.state[KS_EPOCH] += 1; kc.state[KS_CALLS] += 1;
     }
 }
-// pass 1: in-batch de-duplication; representatives also probe the persistent cache (lookup only)
+// pass 1: in-batch de-duplication + use counts; representatives also probe the persistent cache (lookup only)
 __global__ void __launch_bounds__(256)
 k_kc_dedup(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,82 +399,165 @@ k_kc_dedup(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
         h = (h + 1) & kc.bmask;
     }
     kc.rep[i] = r;
+    kc_grouped_add(&kc.cnt[r]);
     if (r != i) return;
-    atomicAdd(&kc.state[3], 1u);
-    // persistent lookup
-    uint32_t id = KC_EMPTY, cached = kc.state[5];
+    kc.dlist[atomicAdd(&kc.state[KS_DISTINCT], 1u)] = i;
+    // persistent lookup (the table holds live ids only: evictions rebuild it)
+    uint32_t id = KC_EMPTY;
     h = h0 & kc.slot_mask;
     for (uint32_t probes = 0; probes <= kc.slot_mask; probes++) {
         uint32_t cur = kc.slots[h];
         if (cur == KC_EMPTY) break;
-        if (cur < cached && kc_equal(w, kc.cpks + 32ull * cur)) { id = cur; break; }
+        if (kc_equal(w, kc.cpks + 32ull * cur)) { id = cur; break; }
         h = (h + 1) & kc.slot_mask;
     }
     kc.kid[i] = id;
-    if (id == KC_EMPTY) atomicAdd(&kc.state[6], 1u);
 }
-__global__ void k_kc_mode(KeyCacheDev kc, uint32_t n) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t cached = kc.state[5], distinct = kc.state[3], missing = kc.state[6];
-    uint32_t build = missing, reset = 0;
-    if (cached + missing > kc.max_keys) { reset = 1; build = distinct; }      // does not fit next to what is cached: start over
-    bool keyed = build <= kc.max_keys && (uint64_t)build * KC_AMORTISE <= n;
-    kc.state[1] = keyed ? 1u : 0u;
-    kc.state[2] = (keyed && reset) ? 1u : 0u;
-}
+// pass 2a, one thread per distinct key: cached -> touch it; frequent enough -> candidate for a table; else cold
 __global__ void __launch_bounds__(256)
-k_kc_reset(KeyCacheDev kc) {
-    if (!kc.state[2]) return;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+k_kc_plan1(KeyCacheDev kc) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kc.state[KS_DISTINCT]) return;
+    const uint32_t r = kc.dlist[j], id = kc.kid[r], c = kc.cnt[r];
+    if (id != KC_EMPTY) { kc.stamp[id] = kc.state[KS_EPOCH]; kc.bucket[id] = c; }
+    else if (c >= KC_AMORTISE) kc.cand[atomicAdd(&kc.state[KS_NCAND], 1u)] = r;
+    else kc.kid[r] = KC_COLD;
+}
+// pass 2b, ONE CTA: make room (least recently used tables first, never one that this call uses), hand out ids
+constexpr int KC_PLAN_THREADS = 1024;
+__device__ __forceinline__ uint32_t kc_block_count_older(const KeyCacheDev& kc, uint32_t high, uint32_t epoch, uint32_t thr, uint32_t* s_cnt) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    for (uint32_t id = threadIdx.x; id < high; id += blockDim.x) { const uint32_t st = kc.stamp[id]; c += (st != 0 && st != epoch && st <= thr); }
+    if (c) atomicAdd(s_cnt, c);
+    __syncthreads();
+    return *s_cnt;
+}
+__global__ void __launch_bounds__(KC_PLAN_THREADS)
+k_kc_plan2(KeyCacheDev kc, const uint8_t* __restrict__ pks) {
+    __shared__ uint32_t s_cnt, s_taken, s_pushed;
+    const uint32_t ncand = kc.state[KS_NCAND], high = kc.state[KS_HIGH], epoch = kc.state[KS_EPOCH];
+    uint32_t nfree = kc.state[KS_NFREE];
+    if (ncand == 0) return;
+    const uint32_t avail0 = (kc.max_keys - high) + nfree;
+    if (ncand > avail0 && epoch > 1) {
+        const uint32_t want = ncand - avail0;
+        // smallest stamp threshold that frees `want` tables (stamps are call numbers: older = smaller)
+        uint32_t lo = 1, hi = epoch - 1;
+        const uint32_t evictable = kc_block_count_older(kc, high, epoch, hi, &s_cnt);
+        if (evictable) {
+            const uint32_t goal = want < evictable ? want : evictable;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if (kc_block_count_older(kc, high, epoch, mid, &s_cnt) >= goal) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t below = lo > 1 ? kc_block_count_older(kc, high, epoch, lo - 1, &s_cnt) : 0;   // all of these go
+            __syncthreads();
+            if (threadIdx.x == 0) { s_taken = 0; s_pushed = 0; }
+            __syncthreads();
+            const uint32_t at_thr = goal - below;                                                        // and this many with stamp == lo
+            for (uint32_t id = threadIdx.x; id < high; id += blockDim.x) {
+                const uint32_t st = kc.stamp[id];
+                if (st == 0 || st == epoch || st > lo) continue;
+                if (st == lo && atomicAdd(&s_taken, 1u) >= at_thr) continue;
+                kc.stamp[id] = 0; kc.valid[id] = 0;
+                kc.free_list[nfree + atomicAdd(&s_pushed, 1u)] = id;
+            }
+            __syncthreads();
+            nfree += s_pushed;
+            if (threadIdx.x == 0) { kc.state[KS_REBUILD] = 1; kc.state[KS_EVICTED] = s_pushed; kc.state[KS_TOTAL_EVICTED] += s_pushed; }
+        }
+    }
+    __syncthreads();
+    const uint32_t avail = (kc.max_keys - high) + nfree;
+    const uint32_t take = ncand < avail ? ncand : avail;
+    for (uint32_t j = threadIdx.x; j < ncand; j += blockDim.x) {
+        const uint32_t r = kc.cand[j];
+        if (j >= take) { kc.kid[r] = KC_COLD; continue; }
+        const uint32_t id = j < nfree ? kc.free_list[nfree - 1 - j] : high + (j - nfree);
+        uint32_t w[8];
+        load_words8(w, pks + 32ull * r);
+        store_words8(kc.cpks + 32ull * id, w);
+        kc.kid[r] = id; kc.stamp[id] = epoch; kc.bucket[id] = kc.cnt[r]; kc.build_list[j] = id;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t from_free = take < nfree ? take : nfree;
+        kc.state[KS_NBUILD] = take; kc.state[KS_NFREE] = nfree - from_free; kc.state[KS_HIGH] = high + (take - from_free);
+        kc.state[KS_TOTAL_BUILT] += take;
+    }
+}
+// the persistent hash table: after an eviction it is cleared and every live id re-inserted, otherwise only the new ids go in
+__global__ void __launch_bounds__(256)
+k_kc_rehash_clear(KeyCacheDev kc) {
+    if (!kc.state[KS_REBUILD]) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t s = t; s <= kc.slot_mask; s += gridDim.x * blockDim.x) kc.slots[s] = KC_EMPTY;
-    if (t == 0) { kc.state[0] = 0; kc.state[5] = 0; }
 }
-// pass 2 (table-driven mode only): representatives not yet cached claim an id, publish their key and queue a build
 __global__ void __launch_bounds__(256)
-k_kc_insert(KeyCacheDev kc, const uint8_t* __restrict__ pks, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !kc.state[1] || kc.rep[i] != i) return;
-    if (kc.state[2]) kc.kid[i] = KC_EMPTY;                    // cache was reset: earlier ids are void
-    if (kc.kid[i] != KC_EMPTY) return;
+k_kc_rehash_insert(KeyCacheDev kc) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t id;
+    if (kc.state[KS_REBUILD]) { if (t >= kc.state[KS_HIGH] || kc.stamp[t] == 0) return; id = t; }
+    else { if (t >= kc.state[KS_NBUILD]) return; id = kc.build_list[t]; }
     uint32_t w[8];
-    load_words8(w, pks + 32ull * i);
-    uint32_t id = atomicAdd(&kc.state[0], 1u);               // cannot exceed max_keys: k_kc_mode checked
-    store_words8(kc.cpks + 32ull * id, w);
+    load_words8(w, kc.cpks + 32ull * id);
     uint32_t h = kc_hash(w) & kc.slot_mask;
     while (atomicCAS(&kc.slots[h], KC_EMPTY, id) != KC_EMPTY) h = (h + 1) & kc.slot_mask;   // distinct keys: no equality test needed
-    kc.kid[i] = id;
-    kc.build_list[atomicAdd(&kc.state[4], 1u)] = id;
 }
-__global__ void __launch_bounds__(32)
-k_kc_bases(KeyCacheDev kc) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!kc.state[1] || t >= kc.state[4]) return;
-    uint32_t id = kc.build_list[t];
-    uint32_t pk[8];
-    load_words8(pk, kc.cpks + 32ull * id);
-    kc.valid[id] = (uint8_t)ge_key_row_bases<AFC_BASES_FE>((ge_p3*)kc.bases + (size_t)t * COMB_ROWS, pk);
+// pass 3: exclusive scan of the per-id credential counts -> scatter cursors; ONE CTA
+__global__ void __launch_bounds__(1024)
+k_kc_scan(KeyCacheDev kc) {
+    __shared__ uint32_t s_part[32], s_carry;
+    const uint32_t high = kc.state[KS_HIGH];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < high; base += 1024) {
+        const uint32_t id = base + threadIdx.x, v = id < high ? kc.bucket[id] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t p = s_part[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, p, d); if (threadIdx.x >= d) p += y; }
+            s_part[threadIdx.x] = p;
+        }
+        __syncthreads();
+        const uint32_t warp_off = (threadIdx.x >> 5) ? s_part[(threadIdx.x >> 5) - 1] : 0;
+        if (id < high) kc.bucket[id] = s_carry + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_part[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kc.state[KS_NHOT] = s_carry;
 }
-__global__ void __launch_bounds__(32)
-k_kc_build(KeyCacheDev kc) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!kc.state[1] || t >= kc.state[4] * COMB_ROWS * KR_PARTS) return;
-    uint32_t r = t / KR_PARTS, part = t % KR_PARTS;
-    uint32_t id = kc.build_list[r / COMB_ROWS], row = r % COMB_ROWS;
-    ge_p3 P = ((const ge_p3*)kc.bases)[r];
-    ge_key_row_slice<FeCall, KR_SLICE>((ge_precomp*)kc.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS, P, (int)part * KR_SLICE);
+__global__ void __launch_bounds__(256)
+k_kc_scatter(KeyCacheDev kc, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = kc.kid[kc.rep[i]];
+    if (id >= KC_COLD) kc.cold[kc_grouped_add(&kc.state[KS_NCOLD])] = i;
+    else kc.perm[kc_grouped_add(&kc.bucket[id])] = i;
 }
 // (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
 // the register allocation of the curve loop around and nothing overlaps that did not already.)
 __global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
-                   uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
-    if (!kc.state[1]) return;
-    table_verify_group([&](uint32_t i, const ge_precomp*& atab) {
-        uint32_t id = kc.kid[kc.rep[i]];
+                   int G, uint8_t* __restrict__ ok) {
+    const uint32_t n_hot = kc.state[KS_NHOT];
+    if (!n_hot) return;
+    const uint32_t T = (n_hot + (uint32_t)G - 1) / (uint32_t)G;
+    table_verify_group([&](uint32_t p) { return kc.perm[p]; }, [&](uint32_t i, const ge_precomp*& atab) {
+        const uint32_t id = kc.kid[kc.rep[i]];
         if (!kc.valid[id]) return false;                     // key does not decode: ok = 0
         atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
         return true;
-    }, comb, sigs, ks, n, T, G, ok);
+    }, comb, sigs, ks, n_hot, T, G, ok);
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index.
@@ -587,7 +829,8 @@ static int pick_expand_group(uint32_t n) { return pick_group_for(n, (const void*
 cudaError_t ed_keycache_clear(const KeyCache& kc, cudaStream_t s, LaunchLog* lg) {
     const uint64_t cnt = (uint64_t)kc.slot_mask + 1;
     AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for((cnt + 3) / 4, 256), 256, 0, s>>>(kc.slots, 0xffffffffu, cnt));
-    AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(kc.state, 0u, 8));
+    AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for(((uint64_t)kc.max_keys + 3) / 4, 256), 256, 0, s>>>(kc.stamp, 0u, kc.max_keys));
+    AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(kc.state, 0u, KS_WORDS));
     return cudaGetLastError();
 }
 
@@ -597,64 +840,100 @@ cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
     AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<blocks_for((uint64_t)BASE_ROWS * BASE_COLS / BASE_CHUNK, 32), 32, 0, s>>>((ge_precomp*)comb));
     return cudaGetLastError();
 }
+static void launch_generic_verify(const ge_precomp* cb, const uint8_t* pks, const uint8_t* sigs, const uint32_t* ks, uint32_t n, uint8_t* ok,
+                                  const uint32_t* list, const uint32_t* n_list, cudaStream_t s, LaunchLog* lg) {
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("AFC_VERIFY_VARIANT"); variant = e ? atoi(e) : 0; }
+    const uint32_t nb = blocks_for(n, ED_THREADS);
+    switch (variant) {
+    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 128, 3><<<nb, 128, 0, s>>>(cb, pks, sigs, ks, n, ok, list, n_list)); break;
+    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 128, 2><<<nb, 128, 0, s>>>(cb, pks, sigs, ks, n, ok, list, n_list)); break;
+    }
+}
+// Stages the table build is cut into (rows per stage = 32 / stages): the rows of stage s are filled on kc.side2 while the
+// doubling chain of stage s + 1 runs on kc.side.
+static int kc_stages() {
+    static int st = -1;
+    if (st < 0) { const char* e = getenv("AFC_KC_STAGES"); st = e ? atoi(e) : 1; if (st != 1 && st != 2 && st != 4) st = 1; }
+    return st;
+}
+static void launch_key_build(const KeyBuild& b, uint32_t max_build, cudaStream_t chain, cudaStream_t rows, const cudaEvent_t* ev_chain,
+                             LaunchLog* lg) {
+    static int chain4 = -1;
+    if (chain4 < 0) { const char* e = getenv("AFC_KC_CHAIN4"); chain4 = e ? atoi(e) : 1; }
+    if (chain4) {
+        // four lanes per key, eight keys per warp, one warp per CTA
+        AFC_LAUNCH(lg, "k_kc_chain4", chain, k_kc_chain4<<<blocks_for((uint64_t)max_build * 4, 32), 32, 0, chain>>>(b));
+        if (chain != rows) { cudaEventRecord(ev_chain[0], chain); cudaStreamWaitEvent(rows, ev_chain[0], 0); }
+        AFC_LAUNCH(lg, "k_kc_rows", rows, k_kc_rows<<<blocks_for((uint64_t)max_build * COMB_ROWS * KR_PARTS, KR_NT), KR_NT, 0, rows>>>(b, 0, COMB_ROWS));
+        return;
+    }
+    const int stages = (chain == rows) ? 1 : kc_stages(), nr = COMB_ROWS / stages;
+    for (int st = 0; st < stages; st++) {
+        // one warp per CTA for the chain: 32 x keys small CTAs spread evenly over the SMs
+        AFC_LAUNCH(lg, "k_kc_chain", chain, k_kc_chain<<<blocks_for(max_build, 32), 32, 0, chain>>>(b, st * nr, nr));
+        if (chain != rows) { cudaEventRecord(ev_chain[st], chain); cudaStreamWaitEvent(rows, ev_chain[st], 0); }
+        AFC_LAUNCH(lg, "k_kc_rows", rows, k_kc_rows<<<blocks_for((uint64_t)max_build * nr * KR_PARTS, KR_NT), KR_NT, 0, rows>>>(b, st * nr, nr));
+    }
+}
 cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off,
                             uint32_t n, uint8_t* ok, uint32_t* scratch_k, const KeyCache* kcp, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     const ge_precomp* cb = (const ge_precomp*)comb;
     const uint32_t nb = blocks_for(n, ED_THREADS);
-    const uint32_t* skip = nullptr;
-    if (!kcp) AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
-    if (kcp) {
-        // Issuer-key cache: de-duplicate, look up, decide on the device, build what is missing, verify through tables.
-        // The cache work runs on kc.side (a HIGH-priority stream: its small CTAs are dispatched as soon as SM slots free up)
-        // while H(R||A||M), which does not depend on the cache, runs on the caller's stream: the table build (IMAD.WIDE-bound,
-        // 1 warp per CTA, low occupancy) and the hashing (ALU-bound) share the SMs.  With equal priorities the block
-        // dispatcher drains the hashing grid first and nothing overlaps (measured).
-        const KeyCache kc = *kcp;
-        const cudaStream_t q = kc.side;
-        cudaError_t e = cudaEventRecord(kc.ev_fork, s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(q, kc.ev_fork, 0);
-        if (e != cudaSuccess) return e;
-        {
-            const uint64_t cnt = (uint64_t)kc.bmask + 1;
-            AFC_LAUNCH(lg, "k_fill_u32", q, k_fill_u32<<<blocks_for((cnt + 3) / 4, 256), 256, 0, q>>>(kc.bslots, 0xffffffffu, cnt));
-        }
-        AFC_LAUNCH(lg, "k_kc_begin", q, k_kc_begin<<<1, 32, 0, q>>>(kc));
-        AFC_LAUNCH(lg, "k_kc_dedup", q, k_kc_dedup<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
-        AFC_LAUNCH(lg, "k_kc_mode", q, k_kc_mode<<<1, 32, 0, q>>>(kc, n));
-        AFC_LAUNCH(lg, "k_kc_reset", q, k_kc_reset<<<64, 256, 0, q>>>(kc));
-        AFC_LAUNCH(lg, "k_kc_insert", q, k_kc_insert<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
-        // at most min(max_keys, n / KC_AMORTISE) tables can be due in one call
-        uint64_t max_build = kc.max_keys < n / KC_AMORTISE ? kc.max_keys : n / KC_AMORTISE;
-        if (max_build)
-            // one warp per CTA: 32 x keys small CTAs spread evenly over the 148 SMs (128-thread CTAs left half of them with
-            // twice the work of the rest: 2.44 ms vs the arithmetic floor of ~1.4 ms for 1024 keys)
-        {
-            AFC_LAUNCH(lg, "k_kc_bases", q, k_kc_bases<<<blocks_for(max_build, 32), 32, 0, q>>>(kc));
-            AFC_LAUNCH(lg, "k_kc_build", q, k_kc_build<<<blocks_for(max_build * COMB_ROWS * KR_PARTS, 32), 32, 0, q>>>(kc));
-        }
-        if ((e = cudaEventRecord(kc.ev_join, q)) != cudaSuccess) return e;
+    if (!kcp) {
         AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
-        if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
-        const int G = pick_group(n, (const void*)k_ed_verify_cached);
-        const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, n, T, G, ok));
-        skip = kc.state + 1;
+        launch_generic_verify(cb, pks, sigs, scratch_k, n, ok, nullptr, nullptr, s, lg);
+        return cudaGetLastError();
     }
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("AFC_VERIFY_VARIANT"); variant = e ? atoi(e) : 0; }
-    switch (variant) {
-    case 1: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeCall, 128, 3><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok, skip)); break;
-    default: AFC_LAUNCH(lg, "k_ed_verify", s, k_ed_verify<FeInline, 128, 2><<<nb, 128, 0, s>>>(cb, pks, sigs, scratch_k, n, ok, skip)); break;
+    // Issuer-key cache: de-duplicate, look up, decide per key on the device, build what is missing, bucket by issuer.
+    // The cache work runs on kc.side / kc.side2 (HIGH-priority streams: their small CTAs are dispatched as soon as SM slots free
+    // up) while H(R||A||M), which does not depend on the cache, runs on the caller's stream: the table build (IMAD.WIDE-bound)
+    // and the hashing (ALU-bound) share the SMs.  With equal priorities the block dispatcher drains the hashing grid first
+    // and nothing overlaps (measured).
+    const KeyCache kc = *kcp;
+    const cudaStream_t q = kc.side, q2 = kc.side2;
+    cudaError_t e = cudaEventRecord(kc.ev_fork, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(q, kc.ev_fork, 0);
+    if (e != cudaSuccess) return e;
+    {
+        const uint64_t cnt = (uint64_t)kc.bmask + 1;
+        AFC_LAUNCH(lg, "k_fill_u32", q, k_fill_u32<<<blocks_for((cnt + 3) / 4, 256), 256, 0, q>>>(kc.bslots, 0xffffffffu, cnt));
+        AFC_LAUNCH(lg, "k_fill_u32", q, k_fill_u32<<<blocks_for(((uint64_t)n + 3) / 4, 256), 256, 0, q>>>(kc.cnt, 0u, n));
     }
+    AFC_LAUNCH(lg, "k_kc_begin", q, k_kc_begin<<<blocks_for((uint64_t)kc.max_keys + 1, 256), 256, 0, q>>>(kc));
+    AFC_LAUNCH(lg, "k_kc_dedup", q, k_kc_dedup<<<blocks_for(n, 256), 256, 0, q>>>(kc, pks, n));
+    AFC_LAUNCH(lg, "k_kc_plan1", q, k_kc_plan1<<<blocks_for(n, 256), 256, 0, q>>>(kc));
+    AFC_LAUNCH(lg, "k_kc_plan2", q, k_kc_plan2<<<1, KC_PLAN_THREADS, 0, q>>>(kc, pks));
+    AFC_LAUNCH(lg, "k_kc_rehash_clear", q, k_kc_rehash_clear<<<64, 256, 0, q>>>(kc));
+    AFC_LAUNCH(lg, "k_kc_rehash_insert", q, k_kc_rehash_insert<<<blocks_for(kc.max_keys, 256), 256, 0, q>>>(kc));
+    // at most min(max_keys, n / KC_AMORTISE) tables can be due in one call
+    const uint32_t max_build = kc.max_keys < n / KC_AMORTISE ? kc.max_keys : n / KC_AMORTISE;
+    if (max_build) {
+        KeyBuild b{kc.cpks, kc.build_list, kc.state + KS_NBUILD, max_build, (ge_p3*)kc.bases, (ge_precomp*)kc.tabs, kc.valid};
+        launch_key_build(b, max_build, q, q2, kc.ev_chain, lg);
+    }
+    AFC_LAUNCH(lg, "k_kc_scan", q, k_kc_scan<<<1, 1024, 0, q>>>(kc));
+    AFC_LAUNCH(lg, "k_kc_scatter", q, k_kc_scatter<<<blocks_for(n, 256), 256, 0, q>>>(kc, n));
+    if (max_build) {
+        if ((e = cudaEventRecord(kc.ev_rows, q2)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(q, kc.ev_rows, 0)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventRecord(kc.ev_join, q)) != cudaSuccess) return e;
+    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+    if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
+    const int G = pick_group(n, (const void*)k_ed_verify_cached);
+    const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
+    AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+    launch_generic_verify(cb, pks, sigs, scratch_k, n, ok, kc.cold, kc.state + KS_NCOLD, s, lg);
     return cudaGetLastError();
 }
 size_t ed_key_table_bytes(uint32_t n_keys) { return sizeof(ge_precomp) * (size_t)n_keys * COMB_ROWS * COMB_COLS; }
-size_t ed_key_bases_bytes(uint32_t n_keys) { return sizeof(ge_p3) * (size_t)n_keys * COMB_ROWS; }
+size_t ed_key_bases_bytes(uint32_t n_keys) { return sizeof(ge_p3) * (size_t)n_keys * COMB_ROWS * KB_PTS; }
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg) {
     if (n_keys == 0) return cudaSuccess;
-    AFC_LAUNCH(lg, "k_ed_key_bases", s, k_ed_key_bases<<<blocks_for(n_keys, 32), 32, 0, s>>>(pks, n_keys, (ge_p3*)bases_scratch, valid));
-    AFC_LAUNCH(lg, "k_ed_key_rows", s, k_ed_key_rows<<<blocks_for((uint64_t)n_keys * COMB_ROWS * KR_PARTS, 32), 32, 0, s>>>(n_keys, (const ge_p3*)bases_scratch, (ge_precomp*)tabs));
+    KeyBuild b{pks, nullptr, nullptr, n_keys, (ge_p3*)bases_scratch, (ge_precomp*)tabs, valid};
+    launch_key_build(b, n_keys, s, s, nullptr, lg);
     return cudaGetLastError();
 }
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,

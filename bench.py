@@ -294,7 +294,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count()
-    ctx.profile_begin(max(256, 96 * (args.steps + 2)))      # per-kernel CUDA events on the launching stream
+    ctx.profile_begin(64 + 32 * args.steps)      # per-kernel CUDA events on the launching stream (one pair per launch, claimed lazily)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

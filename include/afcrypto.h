@@ -83,14 +83,24 @@ int afc_ed25519_verify_batch(afc_ctx* ctx, const uint8_t* pks, const uint8_t* si
 int afc_ed25519_verify_batch_dev(afc_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_sigs, const uint8_t* d_msgs,
                                  const uint64_t* d_msg_off, uint32_t n, uint8_t* d_ok, void* stream);
 
-/* Transparent issuer-key cache behind afc_ed25519_verify_batch[_dev]: the batch's public keys are de-duplicated on the
- * device, looked up in a persistent per-context cache of per-key tables (384 KB per key), missing tables are built when
- * that pays for itself (new keys x ~48 verify-equivalents <= batch size and the cache has room; a full cache is reset), and
- * the table-driven kernel runs instead of the generic one.  Decisions are taken on the device, nothing synchronises, results
- * are bit-identical.  max_keys = 0 disables (always the generic kernel); default 1024, or env AFC_KEYCACHE_MAX_KEYS.
- * afc_keycache_info: cached_keys = tables currently held, last_mode = 1 if the last verify call went through tables. */
+/* Transparent issuer-key cache behind afc_ed25519_verify_batch[_dev]: the batch's public keys are de-duplicated and counted on
+ * the device and looked up in a persistent per-context cache of per-key tables (384 KB per key).  The decision is PER KEY:
+ * a cached key goes through its table; a key that is not cached but signs at least 48 credentials of the batch gets a table
+ * built inside the call (the least recently used tables that this call does not need are evicted when the cache is full);
+ * every other credential is verified by the generic kernel in the same call.  Hot credentials are processed bucketed by
+ * issuer.  Decisions are taken on the device, nothing synchronises, results are bit-identical whichever way a credential goes.
+ * max_keys = 0 disables (always the generic kernel); default 4096 (1.6 GB), or env AFC_KEYCACHE_MAX_KEYS.
+ * afc_keycache_info: cached_keys = tables currently held, last_mode = 1 if the last verify call sent any credential through
+ * tables.  afc_keycache_stats: the split of the last call and the running totals. */
+typedef struct afc_keycache_stats_t {
+    uint32_t max_keys, cached_keys;
+    uint32_t last_hot, last_cold;          /* credentials of the last call verified through tables / by the generic kernel */
+    uint32_t last_distinct, last_built, last_evicted;
+    uint32_t total_built, total_evicted, calls;
+} afc_keycache_stats_t;
 int afc_keycache_configure(afc_ctx* ctx, uint32_t max_keys);
 int afc_keycache_info(afc_ctx* ctx, uint32_t* max_keys, uint32_t* cached_keys, uint32_t* last_mode);
+int afc_keycache_stats(afc_ctx* ctx, afc_keycache_stats_t* out);
 /* forget every cached table (stream-ordered: enqueued on `stream`, ordered after earlier verify calls); memory is kept */
 int afc_keycache_clear(afc_ctx* ctx, void* stream);
 

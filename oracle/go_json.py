@@ -89,3 +89,57 @@ def fill_template(segments, kinds, values) -> bytes:
         out += escape_bytes(v) if kinds[f] == STRING else v
         out += segments[f + 1]
     return bytes(out)
+
+
+def number_bytes(x: float) -> bytes:
+    """json.Marshal(float64): Go stdlib encoding/json/encode.go floatEncoder.encode — strconv.AppendFloat(b, f, fmt, -1, 64) with
+    fmt = 'e' iff |f| < 1e-6 or |f| >= 1e21 (else 'f'), then "e-09" -> "e-9".  Reference values that take this path:
+    VCAudit.Metadata map[string]interface{} after json.Unmarshal (internal/services/vc_service.go:250-251 -> :471-474) and
+    ExecutionWebhookPayload.Result (pkg/types/webhook.go:49).
+    Independent of agentfield_b200/go_json.number (which reads repr() through decimal): here the shortest digit string is found
+    by trying %.{p}e for p = 1..17 until it round-trips (correctly rounded printf), then laid out by hand."""
+    if x != x or x in (float("inf"), float("-inf")):
+        raise ValueError("json: unsupported value")
+    if x == 0:
+        return b"-0" if str(x)[0] == "-" else b"0"
+    sign = b"-" if x < 0 else b""
+    a = abs(x)
+    for p in range(1, 18):
+        t = "%.*e" % (p - 1, a)
+        if float(t) == a:
+            break
+    mant, exp = t.split("e")
+    digits = mant.replace(".", "").rstrip("0") or "0"
+    exp = int(exp)
+    if a < 1e-6 or a >= 1e21:
+        body = digits[0] + ("." + digits[1:] if len(digits) > 1 else "") + "e" + ("-" if exp < 0 else "+")
+        body += ("%02d" % abs(exp))
+        if len(body) >= 4 and body[-4] == "e" and body[-2] == "0":       # Go's clean-up of a two-digit exponent with a leading zero
+            body = body[:-2] + body[-1]
+        return sign + body.encode()
+    if exp >= len(digits) - 1:
+        return sign + (digits + "0" * (exp - len(digits) + 1)).encode()
+    if exp >= 0:
+        return sign + (digits[:exp + 1] + "." + digits[exp + 1:]).encode()
+    return sign + ("0." + "0" * (-exp - 1) + digits).encode()
+
+
+def value_bytes(v) -> bytes:
+    """json.Marshal of an interface{} tree as the reference holds it after json.Unmarshal: nil, bool, float64, string,
+    []interface{}, map[string]interface{} (keys sorted bytewise, encode.go mapEncoder)."""
+    if v is None:
+        return b"null"
+    if v is True:
+        return b"true"
+    if v is False:
+        return b"false"
+    if isinstance(v, (int, float)):
+        return number_bytes(float(v))
+    if isinstance(v, str):
+        return b'"' + escape_bytes(v.encode("utf-8", "surrogatepass")) + b'"'
+    if isinstance(v, (list, tuple)):
+        return b"[" + b",".join(value_bytes(x) for x in v) + b"]"
+    if isinstance(v, dict):
+        ks = sorted(v, key=lambda k: k.encode("utf-8", "surrogatepass"))
+        return b"{" + b",".join(b'"' + escape_bytes(k.encode("utf-8", "surrogatepass")) + b'":' + value_bytes(v[k]) for k in ks) + b"}"
+    raise TypeError(type(v))

@@ -323,6 +323,94 @@ def make_flow():
     dump("reference_flow.json", out)
 
 
+# ----------------------------------------------------------------------------- canonical JSON / workflow VC / webhook cases
+def make_go_cases():
+    """go_cases.json: every input in a form the Go generator (baseline/go/gen_golden_test.go) can rebuild with the reference's
+    own structs and stdlib calls, every expectation from the oracle (oracle/go_json.py, oracle/ref_vc.py).  Covers what the
+    round-1 review found unpinned: float64 formatting (encoding/json floatEncoder), string escaping incl. invalid UTF-8,
+    omitempty members, the metadata map after a json.Unmarshal round trip, error-message truncation inside a rune,
+    WorkflowVCDocument (componentVcIds nil / empty / many, endTime nil / set), the webhook payload + its HMAC header."""
+    import struct
+    from oracle import go_json as OJ, ref_vc as RV
+    rng = np.random.default_rng(0xAF06)
+    out = {"floats": [], "strings": [], "execution_vcs": [], "workflow_vcs": [], "webhooks": []}
+    fl = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1.5, 100.0, 1e6, 123456789.125, 3e-5, 1e-6, 9.999999e-7, 1e-7, 1.5e-10, 1e15, 1e16, 1e17, 1e20,
+          1.2345678901234567e19, 1.2345678901234568e20, 9.999999999999999e20, 1e21, 1.0000000000000002e21, 1e22, 1e100, 1.7976931348623157e308,
+          5e-324, 2.2250738585072014e-308, 1.2345678901234567e-5, 1.2345678901234567e-7, 0.3, 2.0 ** 53, 2.0 ** 53 + 2, 2.0 ** 63, 4.35, 1 / 3,
+          -123.456e-9, 42.0, 5.0, 1024.0]
+    fl += [struct.unpack("<d", rng.bytes(8))[0] for _ in range(60)]
+    for x in fl:
+        if x != x or abs(x) == float("inf"):
+            continue
+        out["floats"].append({"bits": struct.pack(">d", x).hex(), "expect": OJ.number_bytes(x).decode()})
+    strs = ["", "plain", 'quote " backslash \\ slash /', "<script>&amp;</script>", "tab\tnl\ncr\rbs\bff\f", "\x00\x01\x1f\x7f", "é中😀", "\u2028\u2029",
+            "did:key:z6Mk-_", "\ufffd valid replacement char"]
+    raws = [s_.encode("utf-8") for s_ in strs] + [b"\xff", b"\xc3", b"a\xe4\xb8", b"\xf0\x9f\x98", b"\xed\xa0\x80", b"\xc0\xaf", b"\xf4\x90\x80\x80", b"ok\xe2\x80\xa8ok",
+                                                   bytes(range(256))]
+    raws += [rng.bytes(int(rng.integers(1, 40))) for _ in range(20)]
+    for raw in raws:
+        out["strings"].append({"utf8": raw.hex(), "expect": (b'"' + OJ.escape_bytes(raw) + b'"').decode("utf-8")})
+
+    master = bytes.fromhex(json.load(open(os.path.join(OUT, "reference_flow.json")))["master_seed"])
+    paths = ["m/44'/0'", "m/44'/1237'/0'", "m/44'/1237'/0'/0'/0'", "m/44'/1237'/0'/1'/3'"]
+    seeds = [H.derive_seed(master, p_) for p_ in paths]
+    dids = [H.did_key(G.public_key(sd)) for sd in seeds]
+
+    def proof_for(did, sig, created):
+        return {"type": "Ed25519Signature2020", "created": created, "verificationMethod": "%s#key-1" % did, "proofPurpose": "assertionMethod",
+                "proofValue": H.b64url_nopad(sig)}
+    metas = ['{"agentfield_version":"1.0.0","vc_version":"1.0"}', "null", '{"n":5,"f":1.5,"big":100000000000000000000,"tiny":0.00000012,"neg":-0,"e":1e21}',
+             '{"z":[1,2.5,null,true,"<x>"],"a":{"b":{"c":12345678901234567890}}}', '{"k\\u00e9y":"v","K":"V","k":1e-7}']
+    errs = ["", "boom", "x" * 500, "y" * 501, "é" * 250 + "z", "é" * 251, "ab" + "中" * 166 + "cd", "😀" * 126, "<fail> & \"quoted\" \n line"]
+    for i, (mj, em) in enumerate([(metas[i % len(metas)], errs[i % len(errs)]) for i in range(len(errs) + 1)]):
+        who = 1 + i % 3
+        f = {"context": ["https://www.w3.org/2018/credentials/v1", "https://agentfield.example.com/contexts/execution/v1"] if i != 4 else None,
+             "type": ["VerifiableCredential", "AgentFieldExecutionCredential"] if i != 5 else [],
+             "id": "urn:agentfield:vc:vc-%d" % (1789971100759287000 + i), "issuer": dids[who], "issuance_date": "2026-09-21T06:00:%02dZ" % i,
+             "execution_id": "exec_%04d" % i, "workflow_id": "wf_<%d>" % (i // 3), "session_id": "sess_%d" % i,
+             "caller": {"did": dids[who], "type": "agent", "agent_node_did": dids[1]},
+             "target": {"did": dids[3] if i % 2 else "", "agent_node_did": dids[1], "function_name": "summarise&rank" if i % 2 else ""},
+             "input_hash": H.hash_data(H.marshal_data_or_null(b"in-%d" % i)), "output_hash": H.hash_data(H.marshal_data_or_null(None if i % 4 == 0 else b"out")),
+             "timestamp": "2026-09-21T06:00:%02dZ" % i, "duration_ms": int(rng.integers(0, 10 ** 6)), "status": ["succeeded", "failed", "completed"][i % 3],
+             "error_message_input": em, "metadata_json": mj}
+        f["input_data_hash"], f["output_data_hash"] = f["input_hash"], f["output_hash"]
+        g = dict(f, error_message=RV.truncate_error_message(em), metadata=RV.unmarshal_interface(mj))
+        canonical = RV.go_marshal(RV.vc_document_from_fields(g))
+        sig = G.sign(seeds[who], canonical)
+        assert Ed25519PrivateKey.from_private_bytes(seeds[who]).sign(canonical) == sig
+        stored = RV.go_marshal(RV.vc_document_from_fields(g, proof_for(dids[who], sig, f["issuance_date"])))
+        out["execution_vcs"].append(dict(f, seed=seeds[who].hex(), pk=G.public_key(seeds[who]).hex(), proof_created=f["issuance_date"],
+                                         expect_canonical=canonical.decode("utf-8"), expect_sig=sig.hex(), expect_stored=stored.decode("utf-8")))
+    ids_cases = [None, [], ["vc-1"], ["vc-%d" % k for k in range(40)], ["vc-<&>", "vc-\u2028", 'vc-"q"']]
+    for i, ids in enumerate(ids_cases * 2):
+        end = None if i % 2 == 0 else ("" if i == 3 else "2026-09-21T07:00:%02dZ" % i)
+        w = {"workflow_id": "wf_%d" % i, "session_id": "sess_%d" % i if i else "", "component_vc_ids": ids,
+             "status": ["succeeded", "failed", "running", "pending", "timeout"][i % 5], "start_time": "2026-09-21T05:00:%02dZ" % i, "end_time": end,
+             "snapshot_time": "2026-09-21T08:00:%02dZ" % i, "issuer_did": dids[i % 4], "vc_id": "vc-%d" % (1789971100759288000 + i),
+             "issuance_date": "2026-09-21T08:00:%02dZ" % i, "proof_created": "2026-09-21T08:00:%02dZ" % i}
+        r = RV.generate_workflow_vc(w, seeds[i % 4])
+        assert G.sign(seeds[i % 4], r["canonical"]).hex() and RV.verify_workflow_vc(r["vc_document"], G.public_key(seeds[i % 4]))
+        tampered = r["vc_document"].replace(b'"totalSteps":', b'"totalSteps":1', 1) if ids else r["vc_document"].replace(b"wf_", b"wf-", 1)
+        assert not RV.verify_workflow_vc(tampered, G.public_key(seeds[i % 4]))
+        out["workflow_vcs"].append(dict(w, seed=seeds[i % 4].hex(), pk=G.public_key(seeds[i % 4]).hex(), expect_canonical=r["canonical"].decode("utf-8"),
+                                        expect_sig=base64_to_hex(r["signature"]), expect_stored=r["vc_document"].decode("utf-8")))
+    results = [None, '{"ok":true}', '{"score":0.87,"n":3,"items":[1e21,1e-7,2.5]}', '"just a string <b>"', "[1,2,3]", "12.5"]
+    for i, rj in enumerate(results):
+        p_ = {"event": "execution.completed" if i % 2 == 0 else "execution.failed", "execution_id": "exec_%d" % i, "workflow_id": "wf_%d" % i,
+              "status": "succeeded" if i % 2 == 0 else "failed", "target": "node-%d.fn" % i, "type": "reasoner",
+              "duration_ms": None if i == 1 else 1000 + i, "result_json": rj, "error_message": "it <broke>" if i % 2 else None,
+              "timestamp": "2026-09-21T06:30:%02dZ" % i}
+        body = RV.go_marshal(RV.webhook_payload(dict(p_, result=None if rj is None else RV.unmarshal_interface(rj))))
+        secret = "whsec_%d_" % i + "s" * (i * 20)
+        out["webhooks"].append(dict(p_, secret=secret, expect_body=body.decode("utf-8"), expect_header=H.webhook_signature(secret, body)))
+    dump("go_cases.json", out)
+
+
+def base64_to_hex(s):
+    import base64
+    return base64.urlsafe_b64decode(s + "=" * (-len(s) % 4)).hex()
+
+
 if __name__ == "__main__":
     make_rfc8032()
     make_fips180()
@@ -330,4 +418,5 @@ if __name__ == "__main__":
     make_rfc6962()
     make_edge()
     make_flow()
+    make_go_cases()
     print("golden fixtures written to", OUT)

@@ -99,6 +99,36 @@ int hs_key_row_mismatches(const uint8_t pk[32], int i) {
     }
     return bad;
 }
+// The round-2 construction (k_kc_chain + k_kc_rows): the chain in `stages` stages leaving P, 32 P, 64 P per row, slices started
+// from those helpers, forward run / inversion / backward run — against the single-thread form.  The CTA-wide product tree that
+// shares the inversion on the device is replaced here by one inversion per slice (same values); returns mismatching words.
+int hs_key_table_staged_mismatches(const uint8_t pk[32], int stages, int row) {
+    uint32_t p[8]; words_from_bytes(p, pk, 8);
+    static ge_p3 bases3[COMB_ROWS * KB_PTS];
+    static ge_precomp a[COMB_COLS], b[COMB_COLS];
+    const int nr = COMB_ROWS / stages;
+    int ok1 = 1;
+    for (int st = 0; st < stages; st++) { int ok = ge_key_chain_stage(bases3, p, st * nr, nr); if (st == 0) ok1 = ok; }
+    constexpr int PARTS = 4, SL = COMB_COLS / PARTS;
+    for (int part = 0; part < PARTS; part++) {
+        ge_p3 M; ge_cached c;
+        ge_key_slice_start<FeInline, PARTS>(M, c, bases3 + row * KB_PTS, part);
+        fe X[SL], Y[SL], Z[SL], Pz[SL], inv;
+        ge_affine_run_fwd<FeInline, SL>(X, Y, Z, Pz, M, c);
+        fe_invert(inv, Pz[SL - 1]);
+        ge_affine_run_bwd<FeInline, SL>(a + part * SL, X, Y, Z, Pz, inv);
+    }
+    int ok2 = ge_build_key_row(b, p, row);
+    int bad = (ok1 != ok2);
+    if (!ok2) return bad;            // undecodable key: the staged chain substitutes the neutral element, tables are never used
+    for (int j = 0; j < COMB_COLS; j++) {
+        uint32_t x[8], y[8];
+        const fe* u[3] = {&a[j].ypx, &a[j].ymx, &a[j].xy2d};
+        const fe* v[3] = {&b[j].ypx, &b[j].ymx, &b[j].xy2d};
+        for (int q = 0; q < 3; q++) { fe_towords(x, *u[q]); fe_towords(y, *v[q]); for (int w = 0; w < 8; w++) bad += x[w] != y[w]; }
+    }
+    return bad;
+}
 // ge_encode_group (one inversion for G points, run-time G) against ge_encode point by point; returns mismatching words
 int hs_encode_group_mismatches(int G, uint32_t seed) {
     ensure_tables();

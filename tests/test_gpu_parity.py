@@ -253,14 +253,18 @@ def test_keyed_verify_equals_generic_verify_and_go_rules(ctx):
 
 def test_transparent_key_cache_paths(ctx):
     """afc_ed25519_verify_batch with the issuer-key cache: every decision path must give the oracle's bitmap — distinct keys
-    (generic kernel), repeated keys (tables built, then reused), cache overflow (reset + rebuild), more distinct keys than the
-    cache holds (generic), Go-rule edge keys through the table path, and cache disabled."""
+    (all cold: generic kernel), repeated keys (tables built, then reused), a full cache (least recently used tables evicted),
+    more hot keys than the cache holds (some hot, the rest cold IN THE SAME CALL), hot + cold mixes, Go-rule edge keys through
+    the table path, and cache disabled."""
     rng = np.random.default_rng(0xAF77)
 
-    def batch(nk, n, seed_off=0, msg_len=200):
-        seeds = np.random.default_rng(1000 + seed_off).integers(0, 256, (nk, 32), dtype=np.uint8)
+    def batch(nk, n, seed_off=0, msg_len=200, extra_distinct=0):
+        seeds = np.random.default_rng(1000 + seed_off).integers(0, 256, (nk + extra_distinct, 32), dtype=np.uint8)
         kp = ctx.pubkeys(seeds)
-        ki = rng.integers(0, nk, n)
+        ki = rng.integers(0, nk, n + extra_distinct)
+        if extra_distinct:
+            ki[rng.permutation(n + extra_distinct)[:extra_distinct]] = nk + np.arange(extra_distinct)     # keys used exactly once
+        n = n + extra_distinct
         msgs = rng.integers(0, 256, (n, msg_len), dtype=np.uint8)
         off = np.arange(n + 1, dtype=np.uint64) * msg_len
         sigs = ctx.sign_packed(seeds[ki].copy(), msgs.reshape(-1), off)
@@ -269,27 +273,52 @@ def test_transparent_key_cache_paths(ctx):
         pks[5::2500, 2] ^= 1                                 # a few corrupted (mostly off-curve / unknown) keys
         return pks, sigs, msgs.reshape(-1), off
 
-    def check(args, want_mode=None):
+    def check(args):
         pks, sigs, buf, off = args
         got = ctx.verify_packed(pks, sigs, buf, off)
         assert (got == CO.ed25519_verify_batch(pks, sigs, buf, off, 8)).all()
-        info = ctx.keycache_info()
-        if want_mode is not None:
-            assert info["last_mode"] == want_mode, info
-        return info
+        st = ctx.keycache_stats()
+        if st["max_keys"]:
+            assert st["last_hot"] + st["last_cold"] == len(off) - 1, st
+        assert ctx.keycache_info()["last_mode"] == (1 if st["last_hot"] else 0)
+        return st
 
     try:
         ctx.keycache_configure(16)
-        check(batch(3000, 3000, 1), want_mode=0)             # ~all keys distinct: generic kernel
-        i1 = check(batch(10, 6000, 2), want_mode=1)          # 10 keys (+ a few corrupted ones), heavy reuse
-        assert 10 <= i1["cached_keys"] <= 16
+        st = check(batch(3000, 3000, 1))                      # ~all keys distinct: everything cold
+        assert st["last_hot"] == 0 and st["last_built"] == 0 and st["cached_keys"] == 0
+        s1 = check(batch(10, 6000, 2))                        # 10 keys (+ a few corrupted ones: used once, cold), heavy reuse
+        assert s1["last_built"] == 10 and s1["cached_keys"] == 10 and 0 < s1["last_cold"] <= 3
         b = batch(10, 6000, 2)
         b[0][5::2500, 2] ^= 1                                 # same 10 keys, no corrupted ones this time
-        i2 = check(b, want_mode=1)                            # reuse: nothing new to build
-        assert i2["cached_keys"] == i1["cached_keys"]
-        i3 = check(batch(12, 9000, 3), want_mode=1)          # 12 other keys do not fit next to the cached ones: reset + rebuild
-        assert i3["cached_keys"] <= 16
-        check(batch(40, 20000, 4), want_mode=0)              # 40 hot keys > capacity 16: generic kernel
+        s2 = check(b)                                         # reuse: nothing new to build, nothing cold
+        assert s2["last_built"] == 0 and s2["last_cold"] == 0 and s2["cached_keys"] == 10
+        s3 = check(batch(12, 9000, 3))                        # 12 other keys: 6 free ids + 6 least recently used tables evicted
+        assert s3["last_built"] == 12 and s3["last_evicted"] == 6 and s3["cached_keys"] == 16
+        s4 = check(batch(40, 20000, 4))                       # 40 hot keys > capacity 16: 16 get tables, 24 stay cold in the same call
+        assert s4["last_built"] == 16 and s4["last_evicted"] == 16 and s4["cached_keys"] == 16
+        assert 0.4 * 20000 < s4["last_cold"] < 0.8 * 20000 and s4["last_hot"] > 0.2 * 20000
+        s5 = check(batch(8, 8000, 5, extra_distinct=1500))    # 8 hot issuers among 1500 one-off keys
+        assert s5["last_built"] == 8 and s5["last_cold"] >= 1500 and s5["last_hot"] >= 7000
+        # LRU order: capacity 4; A = {a, b, c, d}; B touches {a, b}; C brings {e, f}: c and d go, a and b stay
+        ctx.keycache_configure(4)
+        seeds = np.random.default_rng(77).integers(0, 256, (6, 32), dtype=np.uint8)
+        kp = ctx.pubkeys(seeds)
+
+        def call(which, n=600):
+            ki = np.array(which)[rng.integers(0, len(which), n)]
+            msgs = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+            off = np.arange(n + 1, dtype=np.uint64) * 64
+            sigs = ctx.sign_packed(seeds[ki].copy(), msgs.reshape(-1), off)
+            sigs[::9, 40] ^= 1
+            return check((kp[ki].copy(), sigs, msgs.reshape(-1), off))
+        assert call([0, 1, 2, 3])["last_built"] == 4
+        assert call([0, 1])["last_built"] == 0
+        sc = call([4, 5])
+        assert sc["last_built"] == 2 and sc["last_evicted"] == 2
+        assert call([0, 1, 4, 5])["last_built"] == 0          # the recently used pair survived
+        sd = call([2, 3])
+        assert sd["last_built"] == 2 and sd["last_evicted"] == 2 and sd["total_evicted"] == 4
         ctx.keycache_configure(256)
         es = golden("ed25519_edge.json")
         rep = 120
@@ -298,13 +327,14 @@ def test_transparent_key_cache_paths(ctx):
         from agentfield_b200 import pack
         buf, off = pack([bytes.fromhex(e["msg"]) for e in es] * rep)
         got = ctx.verify_packed(pks, sigs, buf, off)
-        assert ctx.keycache_info()["last_mode"] == 1
+        st = ctx.keycache_stats()
+        assert st["last_hot"] == len(es) * rep and st["last_cold"] == 0          # every edge key went through a table
         assert (got.reshape(rep, -1) == np.array([e["valid"] for e in es], dtype=np.uint8)).all()
         ctx.keycache_configure(0)
-        check(batch(10, 6000, 5), want_mode=0)
-        assert ctx.keycache_info()["max_keys"] == 0
+        st = check(batch(10, 6000, 5))
+        assert st["last_hot"] == 0 and ctx.keycache_info()["max_keys"] == 0
     finally:
-        ctx.keycache_configure(1024)
+        ctx.keycache_configure(4096)
 
 
 def test_expanded_key_cache_derivation_matches_reference_flow(ctx):
@@ -363,6 +393,118 @@ def test_config1_issue_and_verify_1000_vcs_reference_flow(ctx):
                                        "result": None, "error_message": r["error_message"], "timestamp": r["timestamp"]}) for r in reqs[:200]]
     secrets = ["secret-%d" % (i % 5) for i in range(200)]
     assert generate_webhook_signature_batch(secrets, bodies, ctx) == [H.webhook_signature(s, b) for s, b in zip(secrets, bodies)]
+
+
+def test_go_cases_signatures_tags_and_device_canonical_form(ctx):
+    """tests/golden/go_cases.json through the GPU: Ed25519 signatures over the canonical bytes of execution and workflow VCs,
+    verification of the stored documents, webhook HMAC headers, and the three device templates filled by the kernels."""
+    import go_cases_util as U
+    from agentfield_b200 import Signer, Verifier, canonical as CA, go_json as GJ
+    from agentfield_b200.services import generate_webhook_signature_batch
+    g = golden("go_cases.json")
+    cases = [(c, c["expect_canonical"].encode("utf-8")) for c in g["execution_vcs"] + g["workflow_vcs"]]
+    sigs = Signer(ctx).sign_batch([bytes.fromhex(c["seed"]) for c, _ in cases], [m for _, m in cases])
+    assert [s.hex() for s in sigs] == [c["expect_sig"] for c, _ in cases]
+    pks = [bytes.fromhex(c["pk"]) for c, _ in cases]
+    assert Signer(ctx).public_keys([bytes.fromhex(c["seed"]) for c, _ in cases]) == pks
+    assert all(Verifier(ctx).verify_batch(pks, [m for _, m in cases], sigs))
+    assert not any(Verifier(ctx).verify_batch(pks, [m + b" " for _, m in cases], sigs))
+    assert generate_webhook_signature_batch([c["secret"] for c in g["webhooks"]], [c["expect_body"].encode("utf-8") for c in g["webhooks"]], ctx) == \
+        [c["expect_header"] for c in g["webhooks"]]
+    # device templates
+    docs = [U.execution_doc(c) for c in g["execution_vcs"]]
+    t0, t1 = CA.vc_document_template(False, ctx), CA.vc_document_template(True, ctx)
+    assert t0.fill([CA.vc_document_values(d) for d in docs]) == [c["expect_canonical"].encode("utf-8") for c in g["execution_vcs"]]
+    proofs = [U.proof(c["issuer"], bytes.fromhex(c["expect_sig"]), c["proof_created"]) for c in g["execution_vcs"]]
+    assert t1.fill([CA.vc_document_values(d, p) for d, p in zip(docs, proofs)]) == [c["expect_stored"].encode("utf-8") for c in g["execution_vcs"]]
+    wdocs = [U.workflow_doc(c) for c in g["workflow_vcs"]]
+    w0, w1 = CA.workflow_vc_document_template(False, ctx), CA.workflow_vc_document_template(True, ctx)
+    assert w0.fill([CA.workflow_vc_document_values(d) for d in wdocs]) == [c["expect_canonical"].encode("utf-8") for c in g["workflow_vcs"]]
+    wproofs = [U.proof(c["issuer_did"], bytes.fromhex(c["expect_sig"]), c["proof_created"]) for c in g["workflow_vcs"]]
+    assert w1.fill([CA.workflow_vc_document_values(d, p) for d, p in zip(wdocs, wproofs)]) == [c["expect_stored"].encode("utf-8") for c in g["workflow_vcs"]]
+    wt = CA.JsonTemplate(*CA.webhook_payload_template_parts(), ctx)
+    assert wt.fill([CA.webhook_payload_values(U.webhook(c)) for c in g["webhooks"]]) == [c["expect_body"].encode("utf-8") for c in g["webhooks"]]
+
+
+def test_workflow_vc_issue_verify_and_comprehensive_audit(ctx):
+    """The workflow-level credential path (vc_service.go:525-718, 1386-1644): roll 64 workflows of 0..40 execution VCs up into
+    signed WorkflowVCDocuments on the GPU — byte-identical to the CPU restatement (oracle/ref_vc.py, OpenSSL signatures) —
+    verify them from their stored bytes, and run the comprehensive audit of one chain (every signature in one GPU batch):
+    clean chain valid with score 100, each kind of tampering reported the way the reference reports it."""
+    import json
+    from test_host_logic import _vc_requests
+    from agentfield_b200 import ExpandedKeys
+    from agentfield_b200.services import VCService
+    from oracle import ref_vc, go_hash as H
+    rng = np.random.default_rng(0xAF61)
+    master = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    paths = ["m/44'/0'"] + ["m/44'/%d'/0'" % (2000 + a) for a in range(8)]
+    cache = ExpandedKeys(ctx)
+    dids = cache.derive(master, paths)
+    seeds = {d: H.derive_seed(master, p) for d, p in zip(dids, paths)}
+    svc = VCService(cache, ctx)
+    workflows, oracle_in = [], []
+    statuses = ["succeeded", "completed", "failed", "running", "timeout", "pending", "cancelled"]
+    for w in range(64):
+        m = int(rng.integers(0, 41)) if w else 0
+        reqs = _vc_requests(m, dids[1:], rng, pad_to=0)
+        issued = svc.generate_execution_vc_batch(reqs) if m else []
+        evs = [{"vc_id": r["vc_id"], "execution_id": r["execution_id"], "workflow_id": "wf-%d" % w, "session_id": "sess-%d" % w,
+                "status": statuses[int(rng.integers(0, 3 if w % 2 else len(statuses)))], "created_at": "2026-09-21T%02d:%02d:00Z" % (rng.integers(0, 24), rng.integers(0, 60)),
+                "issuer_did": r["caller_did"]} for r in reqs]
+        wf = {"workflow_id": "wf-%d" % w, "execution_vcs": evs, "root_did": dids[0], "vc_id": "vc-%d" % (10 ** 18 + w), "workflow_vc_id": "vc-%d" % (2 * 10 ** 18 + w),
+              "issuance_date": "2026-09-22T00:00:00Z", "snapshot_time": "2026-09-22T00:00:00Z", "proof_created": "2026-09-22T00:00:01Z"}
+        workflows.append(wf)
+    got = svc.generate_workflow_vc_batch(workflows)
+    for wf, g_ in zip(workflows, got):
+        evs = wf["execution_vcs"]
+        from agentfield_b200.services import normalize_execution_status
+        status = ref_vc.determine_workflow_status([normalize_execution_status(e["status"]) for e in evs])
+        times = [e["created_at"] for e in evs]
+        issuer = evs[0]["issuer_did"] if evs else dids[0]
+        o = ref_vc.generate_workflow_vc({"workflow_id": wf["workflow_id"], "session_id": evs[0]["session_id"] if evs else "",
+                                         "component_vc_ids": [e["vc_id"] for e in evs], "status": status,
+                                         "start_time": min(times) if evs else wf["snapshot_time"],
+                                         "end_time": max(times) if evs and status in ("succeeded", "failed", "cancelled", "timeout") else None,
+                                         "snapshot_time": wf["snapshot_time"], "issuer_did": issuer, "vc_id": wf["vc_id"],
+                                         "issuance_date": wf["issuance_date"], "proof_created": wf["proof_created"]}, seeds[issuer])
+        assert g_["vc_document"] == o["vc_document"] and g_["signature"] == o["signature"] and g_["status"] == status
+        assert g_["total_steps"] == len(evs) and g_["document_size_bytes"] == len(o["vc_document"])
+    assert all(svc.verify_workflow_vc_batch(got))
+    assert all(ref_vc.verify_workflow_vc(g_["vc_document"], cache.public_key(g_["issuer_did"])) for g_ in got[:10])
+    tampered = [dict(g_, vc_document=g_["vc_document"].replace(b'"snapshotTime":"2026-09-22', b'"snapshotTime":"2026-09-23', 1)) for g_ in got]
+    assert not any(svc.verify_workflow_vc_batch(tampered))
+    # comprehensive audit of one chain
+    reqs = _vc_requests(200, dids[1:], rng, pad_to=0)
+    for r in reqs:
+        r["workflow_id"], r["session_id"] = "wf-audit", "sess-audit"
+    issued = svc.generate_execution_vc_batch(reqs)
+
+    def record(r, v):
+        return {"vc_id": r["vc_id"], "execution_id": r["execution_id"], "workflow_id": r["workflow_id"], "session_id": r["session_id"],
+                "issuer_did": r["caller_did"], "target_did": r.get("target_did", ""), "caller_did": r["caller_did"], "vc_document": v["vc_document"],
+                "signature": v["signature"], "input_hash": v["input_hash"], "output_hash": v["output_hash"], "status": r["status"]}
+    comps = [record(r, v) for r, v in zip(reqs, issued)]
+    wfvc = svc.generate_workflow_vc_batch([{"workflow_id": "wf-audit", "execution_vcs": [dict(c, created_at="2026-09-21T10:00:00Z") for c in comps],
+                                            "root_did": dids[0], "vc_id": "vc-9", "workflow_vc_id": "vc-10", "issuance_date": "2026-09-22T00:00:00Z",
+                                            "snapshot_time": "2026-09-22T00:00:00Z", "proof_created": "2026-09-22T00:00:01Z"}])[0]
+    res = svc.verify_workflow_vc_comprehensive({"component_vcs": comps, "workflow_vc": wfvc})
+    assert res["valid"] and res["overall_score"] == 100.0 and not res["critical_issues"] and not res["warnings"]
+    assert res["security_analysis"]["key_validation"] and res["security_analysis"]["security_score"] == 100.0
+    # (a) a document altered after signing  (b) metadata that disagrees with the document  (c) a workflow VC signed by someone else
+    bad = [dict(c) for c in comps]
+    bad[3]["vc_document"] = bad[3]["vc_document"].replace(b'"durationMs":', b'"durationMs":1', 1)
+    bad[7]["execution_id"] = "exec-other"
+    bad[11]["signature"] = comps[12]["signature"]
+    bad[20]["vc_document"] = b"{not json"
+    res = svc.verify_workflow_vc_comprehensive({"component_vcs": bad, "workflow_vc": dict(wfvc, vc_document=tampered[0]["vc_document"])})
+    kinds = sorted(i["type"] for i in res["critical_issues"])
+    assert kinds == sorted(["signature_verification_failed", "execution_id_mismatch", "signature_mismatch", "parse_error",
+                            "workflow_signature_verification_failed"]), kinds
+    assert not res["valid"] and not res["security_analysis"]["key_validation"] and not res["integrity_checks"]["field_consistency"]
+    assert sorted(res["security_analysis"]["tamper_evidence"]) == ["execution_id_inconsistency", "signature_inconsistency"]
+    assert res["security_analysis"]["security_score"] == 60.0 and [w["type"] for w in res["warnings"]] == ["tamper_evidence"] * 2
+    assert res["overall_score"] == max(0.0, ((100.0 - 25.0 * 5 - 5.0 * 2) + 60.0) / 2.0)
 
 
 def test_ingest_dispatcher_results_and_audit_log(ctx):

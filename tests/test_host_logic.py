@@ -6,6 +6,7 @@ import socket
 import numpy as np
 import pytest
 
+from conftest import golden
 from oracle import merkle as M
 
 
@@ -181,3 +182,68 @@ def test_vc_document_template_matches_go_json():
               "duration_ms": int(rng.integers(0, 10**6)) if i % 2 else None, "result": {"a": word(), "b": [1, 2.5, None]} if i % 3 else None,
               "error_message": word() if i % 5 == 0 else None, "timestamp": word()}
         assert OJ.fill_template(wp[0], wp[1], CA.webhook_payload_values(pl)) == GJ.webhook_payload(pl)
+
+
+def test_go_cases_host_mirror_reproduces_every_expectation():
+    """tests/golden/go_cases.json (oracle-made, re-pinnable by baseline/go/gen_golden_test.go): the host mirror must write the
+    same bytes — float64 formatting in every range, string escaping incl. invalid UTF-8, omitempty, nil slices, the metadata map
+    after json.Unmarshal, an error message cut inside a rune, WorkflowVCDocument, the webhook payload."""
+    import struct
+    from agentfield_b200 import go_json as GJ
+    import go_cases_util as U
+    g = golden("go_cases.json")
+    for c in g["floats"]:
+        x = struct.unpack(">d", bytes.fromhex(c["bits"]))[0]
+        assert GJ.number(x) == c["expect"], c
+    for c in g["strings"]:
+        assert GJ.string_bytes(bytes.fromhex(c["utf8"])) == c["expect"], c
+    for c in g["execution_vcs"]:
+        doc = U.execution_doc(c)
+        assert GJ.vc_document(doc) == c["expect_canonical"].encode("utf-8"), c["id"]
+        assert GJ.vc_document(doc, U.proof(c["issuer"], bytes.fromhex(c["expect_sig"]), c["proof_created"])) == c["expect_stored"].encode("utf-8")
+    for c in g["workflow_vcs"]:
+        doc = U.workflow_doc(c)
+        assert GJ.workflow_vc_document(doc) == c["expect_canonical"].encode("utf-8"), c["workflow_id"]
+        assert GJ.workflow_vc_document(doc, U.proof(c["issuer_did"], bytes.fromhex(c["expect_sig"]), c["proof_created"])) == c["expect_stored"].encode("utf-8")
+    for c in g["webhooks"]:
+        assert GJ.webhook_payload(U.webhook(c)) == c["expect_body"].encode("utf-8"), c["execution_id"]
+
+
+def test_go_cases_device_templates_reproduce_every_expectation():
+    """The device canonical-form templates (VCDocument, WorkflowVCDocument, webhook payload) filled by the byte-level oracle of
+    the device routine give the same bytes (no GPU needed; the kernels are checked against the same oracle in the GPU tier)."""
+    from agentfield_b200 import canonical as CA
+    from oracle import go_json as OJ
+    import go_cases_util as U
+    g = golden("go_cases.json")
+    p0, p1 = CA.vc_document_template_parts(False), CA.vc_document_template_parts(True)
+    for c in g["execution_vcs"]:
+        doc = U.execution_doc(c)
+        assert OJ.fill_template(p0[0], p0[1], CA.vc_document_values(doc)) == c["expect_canonical"].encode("utf-8")
+        pr = U.proof(c["issuer"], bytes.fromhex(c["expect_sig"]), c["proof_created"])
+        assert OJ.fill_template(p1[0], p1[1], CA.vc_document_values(doc, pr)) == c["expect_stored"].encode("utf-8")
+    w0, w1 = CA.workflow_vc_document_template_parts(False), CA.workflow_vc_document_template_parts(True)
+    for c in g["workflow_vcs"]:
+        doc = U.workflow_doc(c)
+        assert OJ.fill_template(w0[0], w0[1], CA.workflow_vc_document_values(doc)) == c["expect_canonical"].encode("utf-8")
+        pr = U.proof(c["issuer_did"], bytes.fromhex(c["expect_sig"]), c["proof_created"])
+        assert OJ.fill_template(w1[0], w1[1], CA.workflow_vc_document_values(doc, pr)) == c["expect_stored"].encode("utf-8")
+    wp = CA.webhook_payload_template_parts()
+    for c in g["webhooks"]:
+        assert OJ.fill_template(wp[0], wp[1], CA.webhook_payload_values(U.webhook(c))) == c["expect_body"].encode("utf-8")
+
+
+def test_workflow_status_roll_up_and_normalisation():
+    """determineWorkflowStatus / NormalizeExecutionStatus / countCompletedSteps (vc_service.go:721-787, pkg/types/status.go:28-75)."""
+    from agentfield_b200 import services as S
+    from oracle import ref_vc as RV
+    assert [S.normalize_execution_status(x) for x in (" Completed ", "OK", "errored", "canceled", "timed_out", "waiting", "in_progress", "", "bogus", "SUCCEEDED")] == \
+        ["succeeded", "succeeded", "failed", "cancelled", "timeout", "queued", "running", "unknown", "unknown", "succeeded"]
+    assert S.is_terminal_execution_status("done") and not S.is_terminal_execution_status("processing")
+    rng = np.random.default_rng(5)
+    pool = ["succeeded", "completed", "failed", "error", "timeout", "cancelled", "running", "queued", "pending", "weird", ""]
+    for _ in range(300):
+        evs = [{"status": pool[int(i)]} for i in rng.integers(0, len(pool), int(rng.integers(0, 6)))]
+        assert S.determine_workflow_status(evs) == RV.determine_workflow_status([S.normalize_execution_status(e["status"]) for e in evs])
+        assert S.count_completed_steps(evs) == sum(e["status"] in ("succeeded", "completed") for e in evs)
+    assert S.determine_workflow_status([]) == "pending"

@@ -131,6 +131,19 @@ def test_key_table_two_step_build_equals_single_thread_rows(hostsim):
         assert hostsim.hs_key_row_mismatches(pk, i) == 0, i
 
 
+def test_key_table_staged_chain_and_helper_starts_equal_single_thread_rows(hostsim):
+    """Round-2 table build: staged doubling chain leaving P, 32 P, 64 P per row, slices started from the helpers,
+    forward / inversion / backward run — equals each row built from A by one thread, for every staging."""
+    for e in golden("rfc8032.json")[:2]:
+        pk = bytes.fromhex(e["pk"])
+        for stages in (1, 2, 4):
+            for row in (0, 7, 8, 19, 31):
+                assert hostsim.hs_key_table_staged_mismatches(pk, stages, row) == 0, (stages, row)
+    # a key that does not decode: flagged, nothing else to compare
+    bad = next(bytes.fromhex(e["pk"]) for e in golden("ed25519_edge.json") if "not on curve" in e["name"])
+    assert hostsim.hs_key_table_staged_mismatches(bad, 4, 3) == 0
+
+
 def test_go_json_escaping_and_template_fill(hostsim):
     """Device routine for Go encoding/json string escaping (afc_json.cuh) vs the byte-level oracle: every single byte, every
     byte pair around the UTF-8 boundaries, random strings at every alignment, and documents assembled from a template."""
