@@ -32,6 +32,8 @@ SYMBOLS = {
     "afc_launch_count": (C.c_uint64, [vp]),
     "afc_alloc_pinned": (vp, [C.c_size_t]),
     "afc_free_pinned": (None, [vp]),
+    "afc_alloc_pinned_for": (vp, [vp, C.c_size_t]),
+    "afc_numa_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "afc_sha256_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
     "afc_sha256_batch_dev": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_hmac_sha256_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp]),
@@ -46,6 +48,7 @@ SYMBOLS = {
     "afc_ed25519_expand_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
     "afc_ed25519_sign_expanded_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]),
     "afc_ed25519_sign_expanded_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
+    "afc_ed25519_sign_expanded_keys_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_keycache_configure": (C.c_int, [vp, C.c_uint32]),
     "afc_keycache_info": (C.c_int, [vp, u32p, u32p, u32p]),
     "afc_keycache_clear": (C.c_int, [vp, vp]),

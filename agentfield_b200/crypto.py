@@ -74,6 +74,11 @@ class Context:
         _abi.check(self._lib.afc_device_info(self.handle, C.byref(sm), C.byref(khz), C.byref(mem)))
         return {"sm_count": sm.value, "clock_khz": khz.value, "mem_bytes": mem.value}
 
+    def numa_info(self):
+        node, cpus = C.c_int(), C.c_int()
+        _abi.check(self._lib.afc_numa_info(self.handle, C.byref(node), C.byref(cpus)))
+        return {"numa_node": node.value, "local_cpus": cpus.value}
+
     def launch_count(self):
         return int(self._lib.afc_launch_count(self.handle))
 

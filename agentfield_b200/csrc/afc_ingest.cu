@@ -70,8 +70,9 @@ struct afc_ingest {
 
 namespace {
 
-bool alloc_batch(Batch& B, uint32_t bm, uint32_t mm, uint32_t mk, uint32_t mb) {
-    auto pin = [](void* p, size_t n) { return cudaHostAlloc((void**)p, n, cudaHostAllocDefault) == cudaSuccess; };
+bool alloc_batch(afc_ctx* ctx, Batch& B, uint32_t bm, uint32_t mm, uint32_t mk, uint32_t mb) {
+    // staging on the NUMA node of the dispatcher's GPU, whichever thread creates it
+    auto pin = [ctx](void* p, size_t n) { return (*(void**)p = afc_internal_pinned_alloc(ctx, n)) != nullptr; };
     auto dev = [](void* p, size_t n) { return cudaMalloc((void**)p, n) == cudaSuccess; };
     size_t n1 = (size_t)bm + 1;
     B.ts.resize(bm);
@@ -98,7 +99,7 @@ int process(afc_ingest* g, Batch& B) {
     cp(B.d_msgs, B.h_msgs, B.msg_bytes); cp(B.d_moff, B.h_moff, (size_t)(n + 1) * 8); cp(B.d_ki, B.h_ki, (size_t)n * 4);
     cp(B.d_keys, B.h_keys, B.key_bytes); cp(B.d_koff, B.h_koff, (size_t)(n + 1) * 4);
     cp(B.d_bodies, B.h_bodies, B.body_bytes); cp(B.d_boff, B.h_boff, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = launch::ed_sign_expanded_batch(afc_internal_comb(g->ctx), g->d_expanded, B.d_ki, B.d_msgs, B.d_moff, n, B.d_sigs, st, &lg);
+    if (e == cudaSuccess) e = launch::ed_sign_expanded_batch(afc_internal_comb(g->ctx), g->d_expanded, g->n_keys, B.d_ki, B.d_msgs, B.d_moff, n, B.d_sigs, st, &lg);
     if (e == cudaSuccess) e = launch::hmac_sha256_batch(B.d_keys, B.d_koff, B.d_bodies, B.d_boff, n, B.d_tags, st, &lg);
     afc_internal_add_launches(g->ctx, lg.n);
     if (e != cudaSuccess) return AFC_ECUDA;
@@ -182,9 +183,9 @@ int afc_ingest_new(afc_ctx* ctx, const uint8_t* expanded96, uint32_t n_keys, uin
               cudaMalloc((void**)&g->d_expanded, (size_t)n_keys * 96) == cudaSuccess &&
               cudaMemcpy(g->d_expanded, expanded96, (size_t)n_keys * 96, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&g->d_sigoff, ((size_t)batch_max + 1) * 8) == cudaSuccess &&
-              cudaHostAlloc((void**)&g->r_sig, (size_t)g->ring * 64, cudaHostAllocDefault) == cudaSuccess &&
-              cudaHostAlloc((void**)&g->r_tag, (size_t)g->ring * 32, cudaHostAllocDefault) == cudaSuccess &&
-              alloc_batch(g->b[0], batch_max, max_msg, g->max_key, max_body) && alloc_batch(g->b[1], batch_max, max_msg, g->max_key, max_body) &&
+              (g->r_sig = (uint8_t*)afc_internal_pinned_alloc(ctx, (size_t)g->ring * 64)) != nullptr &&
+              (g->r_tag = (uint8_t*)afc_internal_pinned_alloc(ctx, (size_t)g->ring * 32)) != nullptr &&
+              alloc_batch(ctx, g->b[0], batch_max, max_msg, g->max_key, max_body) && alloc_batch(ctx, g->b[1], batch_max, max_msg, g->max_key, max_body) &&
               afc_merkle_new(ctx, &g->log) == AFC_OK;
     if (ok) {
         std::vector<uint64_t> so((size_t)batch_max + 1);

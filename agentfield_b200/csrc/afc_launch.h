@@ -127,7 +127,9 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
                                   uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                           uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
-cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, const uint32_t* key_index, const uint8_t* msgs,
+// n_keys bounds key_index on the device (an index >= n_keys signs with key 0 instead of reading out of bounds; the host entry
+// point has already rejected such a batch, the device-pointer one cannot look)
+cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index, const uint8_t* msgs,
                                    const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
 cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
                             cudaStream_t s, LaunchLog* lg);

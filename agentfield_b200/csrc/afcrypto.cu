@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <sched.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -48,14 +49,15 @@ struct DevBuf {
 struct PinBuf {
     uint8_t* p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t n) {
+    cudaError_t reserve(size_t n, afc_ctx* ctx) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = n + n / 4 + 256;
-        cudaError_t e = cudaHostAlloc((void**)&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
+        p = (uint8_t*)afc_internal_pinned_alloc(ctx, want);        // on the NUMA node of the context's GPU
+        if (!p) return cudaErrorMemoryAllocation;
+        cap = want;
+        return cudaSuccess;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
@@ -82,6 +84,10 @@ struct afc_ctx {
     std::condition_variable cv;
     std::atomic<unsigned long long> launches{0};
     std::string last_error;
+    // CPUs next to this GPU (sysfs local_cpulist of its PCI device): pinned staging is allocated from a thread bound to them
+    cpu_set_t local_cpus;
+    bool has_local_cpus = false;
+    int numa_node = -1;
     // transparent issuer-key cache behind afc_ed25519_verify_batch (see k_ed25519.cu)
     launch::KeyCache kc{};
     bool kc_ready = false;
@@ -276,11 +282,28 @@ struct BatchArgs {
 };
 
 // Generic chunked pipeline for host-buffer calls: a ring of kSlots chunks in flight so the H2D of later chunks overlaps the kernels of earlier ones.
+// offsets must be non-decreasing: a caller's slip would otherwise turn into an out-of-bounds copy from its own buffer
+template <class T>
+bool monotone(const T* off, uint32_t n) {
+    T bad = 0;
+    for (uint32_t i = 0; i < n; i++) bad |= (T)(off[i + 1] < off[i]);
+    return bad == 0;
+}
+// On ANY exit of a host-buffer call — error paths included — nothing may still be reading the caller's buffers or writing its
+// results: drain every stream of the lane before it is handed to the next caller.
+struct LaneDrain {
+    Lane& lane; bool armed = true;
+    explicit LaneDrain(Lane& l) : lane(l) {}
+    ~LaneDrain() { if (armed) for (int w = 0; w < kSlots; w++) cudaStreamSynchronize(lane.slot[w].stream); }
+};
+
 int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     if (A.n == 0) return AFC_OK;
+    if (!monotone(A.off, A.n) || (A.koff && !monotone(A.koff, A.n))) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));
     LaneGuard lg(ctx);
     Lane& lane = lg.lane();
+    LaneDrain drain_on_exit(lane);
     const bool pin_msgs = is_pinned(A.msgs), pin_off = is_pinned(A.off), pin_out = is_pinned(A.out);
     const bool pin_a = A.a ? is_pinned(A.a) : true, pin_b = A.b ? is_pinned(A.b) : true;
     const bool pin_keys = A.keys ? is_pinned(A.keys) : true, pin_koff = A.koff ? is_pinned(A.koff) : true;
@@ -336,8 +359,8 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         if (A.b && !pin_b) bounce += ((size_t)cnt * A.b_item + 255) & ~(size_t)255;
         if (A.op == OP_HMAC) { if (!pin_keys) bounce += (kbytes + 255) & ~(size_t)255; if (!pin_koff) bounce += ((size_t)(cnt + 1) * 4 + 255) & ~(size_t)255; }
         if ((A.op == OP_SIGN_EXP || A.op == OP_VERIFY_KEYED) && A.key_index && !pin_ki) bounce += ((size_t)cnt * 4 + 255) & ~(size_t)255;
-        CK(sl.h_in.reserve(bounce + 256));
-        if (!pin_out) CK(sl.h_out.reserve((size_t)cnt * A.out_item));
+        CK(sl.h_in.reserve(bounce + 256, ctx));
+        if (!pin_out) CK(sl.h_out.reserve((size_t)cnt * A.out_item, ctx));
         size_t used = 0;
         // keep the device copy of the messages congruent mod 16 with the absolute offsets so that the kernels see the
         // same alignment whatever the chunking (d_base + off[i] == sl.msgs.p + pad + off[i] - base)
@@ -371,7 +394,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         case OP_SIGN_EXP: {
             const uint32_t* d_ki = nullptr;
             if (A.key_index) { CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used)); d_ki = (const uint32_t*)sl.koff.p; }
-            e = launch::ed_sign_expanded_batch(ctx->comb, A.d_expanded + (A.key_index ? 0 : (size_t)i0 * 96), d_ki, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
+            e = launch::ed_sign_expanded_batch(ctx->comb, A.d_expanded + (A.key_index ? 0 : (size_t)i0 * 96), 0xffffffffu, d_ki, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
             break;
         }
         }
@@ -386,10 +409,54 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         int rc = drain((which + w) % kSlots);
         if (rc != AFC_OK) return rc;
     }
+    drain_on_exit.armed = false;            // every slot was drained above
     return AFC_OK;
 }
 
 }  // namespace
+
+// Binds the CALLING THREAD to the CPUs next to ctx's GPU for the lifetime of the scope: pages allocated (and pinned) meanwhile
+// land on that GPU's NUMA node.  One process driving 8 contexts (the Go control plane) otherwise stages half of its batches
+// through the far socket: measured in round 1 as 37 instead of 55 GB/s per GPU at 8 GPUs.
+struct NumaScope {
+    cpu_set_t old; bool active = false;
+    explicit NumaScope(afc_ctx* ctx) {
+        static const bool off = [] { const char* e = getenv("AFC_NUMA_BIND"); return e && atoi(e) == 0; }();
+        if (!ctx || !ctx->has_local_cpus || off) return;
+        if (sched_getaffinity(0, sizeof old, &old) != 0) return;
+        cpu_set_t want; CPU_AND(&want, &old, &ctx->local_cpus);
+        if (CPU_COUNT(&want) == 0 || CPU_EQUAL(&want, &old)) return;
+        active = sched_setaffinity(0, sizeof want, &want) == 0;
+    }
+    ~NumaScope() { if (active) sched_setaffinity(0, sizeof old, &old); }
+};
+void* afc_internal_pinned_alloc(afc_ctx* ctx, size_t bytes) {
+    NumaScope ns(ctx);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+static void numa_discover(afc_ctx* ctx) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    std::string base = std::string("/sys/bus/pci/devices/") + bus;
+    if (FILE* f = fopen((base + "/numa_node").c_str(), "r")) { if (fscanf(f, "%d", &ctx->numa_node) != 1) ctx->numa_node = -1; fclose(f); }
+    FILE* f = fopen((base + "/local_cpulist").c_str(), "r");
+    if (!f) return;
+    char line[4096] = {0};
+    if (fgets(line, sizeof line, f)) {
+        CPU_ZERO(&ctx->local_cpus);
+        int n = 0;
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &ctx->local_cpus); n++; } }
+            else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) { CPU_SET(a, &ctx->local_cpus); n++; }
+        }
+        ctx->has_local_cpus = n > 0;
+    }
+    fclose(f);
+}
 
 int afc_internal_device(afc_ctx* ctx) { return ctx->device; }
 const void* afc_internal_comb(afc_ctx* ctx) { return ctx->comb; }
@@ -427,6 +494,7 @@ int afc_init(int device, afc_ctx** out) {
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
     if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    numa_discover(ctx);
     {   // per-call scratch comes from the stream-ordered pool: keep freed blocks across synchronisations instead of returning them to
         // the driver (the default threshold of 0 re-maps the 32 MB of a 1 M-credential call after every sync)
         cudaMemPool_t pool = nullptr;
@@ -485,6 +553,13 @@ void* afc_alloc_pinned(size_t bytes) {
     return p;
 }
 void afc_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+void* afc_alloc_pinned_for(afc_ctx* ctx, size_t bytes) { return ctx ? afc_internal_pinned_alloc(ctx, bytes) : nullptr; }
+int afc_numa_info(afc_ctx* ctx, int* numa_node, int* local_cpus) {
+    if (!ctx) return AFC_EINVAL;
+    if (numa_node) *numa_node = ctx->numa_node;
+    if (local_cpus) *local_cpus = ctx->has_local_cpus ? CPU_COUNT(&ctx->local_cpus) : 0;
+    return AFC_OK;
+}
 
 // ---------------------------------------------------------------------------------- host-buffer batch calls
 int afc_sha256_batch(afc_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, uint8_t* out32) {
@@ -543,6 +618,7 @@ int afc_ed25519_sign_expanded_batch(afc_ctx* ctx, const uint8_t* expanded96, con
         BatchArgs A{}; A.op = OP_SIGN_EXP; A.msgs = msgs; A.off = msg_off; A.n = n; A.d_expanded = d_keys; A.key_index = key_index; A.out = sigs; A.out_item = 64;
         rc = run_host_batch(ctx, A);
     } else set_err(ctx, e, "cudaMemcpy(expanded keys)");
+    cudaMemset(d_keys, 0, (size_t)n_keys * 96);       // expanded private keys do not outlive the call on the device
     cudaFree(d_keys);
     return rc;
 }
@@ -601,9 +677,13 @@ int afc_ed25519_expand_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t 
 }
 int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, const uint32_t* d_key_index,
                                         const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream) {
+    return afc_ed25519_sign_expanded_keys_batch_dev(ctx, d_expanded96, 0xffffffffu, d_key_index, d_msgs, d_msg_off, n, d_sigs, stream);
+}
+int afc_ed25519_sign_expanded_keys_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, uint32_t n_keys, const uint32_t* d_key_index,
+                                             const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream) {
     DEV_PROLOGUE();
-    if (!aligned16(d_expanded96) || !aligned16(d_sigs)) return AFC_EINVAL;
-    CK(launch::ed_sign_expanded_batch(ctx->comb, d_expanded96, d_key_index, d_msgs, d_msg_off, n, d_sigs, st, lc));
+    if (!aligned16(d_expanded96) || !aligned16(d_sigs) || n_keys == 0) return AFC_EINVAL;
+    CK(launch::ed_sign_expanded_batch(ctx->comb, d_expanded96, n_keys, d_key_index, d_msgs, d_msg_off, n, d_sigs, st, lc));
     DEV_EPILOGUE();
 }
 int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, uint8_t* d_out32, void* stream) {
@@ -851,10 +931,12 @@ int afc_merkle_append_dev(afc_merkle* m, const uint8_t* d_leaves, const uint64_t
     if (n == 0) return AFC_OK;
     CallLog lc(ctx);
     CK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev, 0));
-    CK(m->lv[1].reserve((size_t)n * 32));
-    CK(launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, m->lv[1].p, (cudaStream_t)stream, lc));
-    int rc = merkle_append_hashes_locked(m, m->lv[1].p, n, (cudaStream_t)stream);
-    CK(cudaEventRecord(m->ev, (cudaStream_t)stream));
+    int rc = AFC_ECUDA;
+    cudaError_t e = m->lv[1].reserve((size_t)n * 32);
+    if (e == cudaSuccess) e = launch::merkle_leaf_hashes(d_leaves, d_leaf_off, n, m->lv[1].p, (cudaStream_t)stream, lc);
+    if (e == cudaSuccess) rc = merkle_append_hashes_locked(m, m->lv[1].p, n, (cudaStream_t)stream);
+    else set_err(ctx, e, "afc_merkle_append_dev");
+    cudaEventRecord(m->ev, (cudaStream_t)stream);      // whatever was enqueued must order the next user of the log, also after a failure
     return rc;
 }
 int afc_merkle_root_dev(afc_merkle* m, uint8_t* d_root32, void* stream) {
@@ -893,6 +975,7 @@ int afc_merkle_append(afc_merkle* m, const uint8_t* leaves, const uint64_t* leaf
     std::lock_guard<std::mutex> g(m->mu);
     CK(cudaStreamWaitEvent(m->stream, m->ev, 0));
     if (n) {
+        if (!monotone(leaf_off, n)) return AFC_EINVAL;
         uint64_t base = leaf_off[0], bytes = leaf_off[n] - base;
         if (bytes && !leaves) return AFC_EINVAL;
         size_t pad = (size_t)(base & 15);

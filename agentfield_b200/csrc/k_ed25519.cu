@@ -86,7 +86,10 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
 // launch parameter: every thread does the same work, so a launch runs in whole waves of `resident threads`; pick_group() chooses
 // G in [1, KC_GMAX] so that the last wave is full and the inversion share small (1 M credentials on 148 SMs x 512 threads: G = 7,
 // 1.9 waves, 4.21 ms; fixed G = 4, 3.3 waves, 4.35 ms; a 65 536-credential chunk of a host call: G = 1, one wave).
-constexpr int KC_GMAX = 8;
+#ifndef AFC_KC_GMAX
+#define AFC_KC_GMAX 16
+#endif
+constexpr int KC_GMAX = AFC_KC_GMAX;
 #ifndef AFC_CACHED_MINB
 #define AFC_CACHED_MINB 3      // 5 (96 registers, 20 warps/SM) was measured: 4.5 ms, spills
 #endif
@@ -103,6 +106,7 @@ __device__ __forceinline__ void table_verify_group(Item item, Lookup lookup, con
     if (t >= T) return;
     fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
     uint32_t good = 0;
+    static_assert(KC_GMAX <= 32, "one bit of `good` per credential of a thread");
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
         uint64_t p = (uint64_t)t + (uint64_t)g * T;
@@ -566,10 +570,11 @@ k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const ui
 // field work of a signature from an expanded key (16 mixed additions = 112 multiplications against 265) and twice that from a seed.
 constexpr int SIGN_GMAX = 8;
 __global__ void __launch_bounds__(ED_THREADS)
-k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, int mode,
+k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, uint32_t n_keys,
           const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ sigs) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
+    const int mode = n_keys != 0;                                 // n_keys = 0: `keys` are seeds, one per credential
     fe X[2 * SIGN_GMAX], Y[2 * SIGN_GMAX], Z[2 * SIGN_GMAX];     // [0, G): R points; [G, 2G): A points (mode 0)
     uint32_t sc[SIGN_GMAX][8], rr[SIGN_GMAX][8], pks[SIGN_GMAX][8];
 #pragma unroll 1
@@ -587,7 +592,9 @@ k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys,
             ge_scalarmult_base<FeCall>(A, sr, comb);
             fe_copy(X[G + g], A.X); fe_copy(Y[G + g], A.Y); fe_copy(Z[G + g], A.Z);
         } else {
-            const uint8_t* e = keys + 96ull * (key_index ? key_index[i] : (uint32_t)i);
+            uint32_t kidx = key_index ? key_index[i] : (uint32_t)i;
+            if (kidx >= n_keys) kidx = 0;                         // never read key material out of bounds
+            const uint8_t* e = keys + 96ull * kidx;
             load_words8(sc[g], e); load_words8(prefix, e + 32); load_words8(pks[g], e + 64);
         }
         const uint64_t o0 = off[i], o1 = off[i + 1];
@@ -951,15 +958,15 @@ cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t*
     if (n == 0) return cudaSuccess;
     const int G = pick_sign_group(n);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, nullptr, 0, msgs, off, n, T, G, sigs));
+    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, nullptr, 0u, msgs, off, n, T, G, sigs));
     return cudaGetLastError();
 }
-cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, const uint32_t* key_index, const uint8_t* msgs,
+cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index, const uint8_t* msgs,
                                    const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     const int G = pick_sign_group(n);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, expanded96, key_index, 1, msgs, off, n, T, G, sigs));
+    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, expanded96, key_index, n_keys, msgs, off, n, T, G, sigs));
     return cudaGetLastError();
 }
 cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,

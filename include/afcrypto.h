@@ -53,6 +53,12 @@ uint64_t afc_launch_count(afc_ctx* ctx);
 /* pinned host staging for the adapter's packing buffers (cudaHostAlloc / cudaFreeHost) */
 void* afc_alloc_pinned(size_t bytes);
 void afc_free_pinned(void* p);
+/* the same, but with the pages on the NUMA node of ctx's GPU whichever thread calls (the calling thread is bound to the CPUs in
+ * /sys/bus/pci/devices/<gpu>/local_cpulist for the duration of the allocation): what a single process driving several contexts —
+ * the Go control plane — uses for its packing pools; the library's own staging buffers are allocated the same way.
+ * afc_numa_info: the GPU's NUMA node (-1 if unknown) and the number of CPUs next to it.  AFC_NUMA_BIND=0 disables the binding. */
+void* afc_alloc_pinned_for(afc_ctx* ctx, size_t bytes);
+int afc_numa_info(afc_ctx* ctx, int* numa_node, int* local_cpus);
 
 /* ---- H1/H2: SHA-256 -----------------------------------------------------------------------------
  * replaces sha256.Sum256 in VCService.hashData (internal/services/vc_service.go:508-515), the
@@ -143,6 +149,10 @@ int afc_ed25519_expand_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t 
 int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, const uint32_t* d_key_index,
                                         const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n,
                                         uint8_t* d_sigs, void* stream);
+/* the same with the number of keys stated: an index >= n_keys can then not read key material out of bounds (it signs with key 0;
+ * the host-buffer call rejects such a batch with AFC_EINVAL, a device-side index array cannot be inspected without a sync) */
+int afc_ed25519_sign_expanded_keys_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, uint32_t n_keys, const uint32_t* d_key_index,
+                                             const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream);
 
 /* ---- M1: RFC 6962 Merkle audit log (NEW — the reference's chain check is a stub,
  * internal/cli/vc_verification_enhanced.go:531-534; nearest code generateWorkflowVCDocument,

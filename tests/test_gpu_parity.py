@@ -139,6 +139,28 @@ def test_empty_batches(ctx):
     a.close()
 
 
+def test_argument_validation_through_the_abi(ctx):
+    """Bad arguments come back as AFC_EINVAL instead of being dereferenced: offsets that run backwards (a slip of the caller's
+    packing code would otherwise become an out-of-bounds copy), key indices past the key set, NULL result buffers."""
+    from agentfield_b200 import AfcError, _abi
+    lib, H = _abi.load(), ctx.handle
+    buf = np.zeros(4096, dtype=np.uint8)
+    out = np.zeros((3, 64), dtype=np.uint8)
+    bad_off = np.array([0, 512, 256, 1024], dtype=np.uint64)
+    seeds = np.zeros((3, 32), dtype=np.uint8)
+    assert lib.afc_sha256_batch(H, _abi.ptr(buf), _abi.ptr(bad_off), 3, _abi.ptr(out)) == _abi.AFC_EINVAL
+    assert lib.afc_ed25519_sign_batch(H, _abi.ptr(seeds), _abi.ptr(buf), _abi.ptr(bad_off), 3, _abi.ptr(out)) == _abi.AFC_EINVAL
+    good_off = np.array([0, 256, 512, 1024], dtype=np.uint64)
+    bad_koff = np.array([0, 32, 16, 64], dtype=np.uint32)
+    assert lib.afc_hmac_sha256_batch(H, _abi.ptr(buf), _abi.ptr(bad_koff), _abi.ptr(buf), _abi.ptr(good_off), 3, _abi.ptr(out)) == _abi.AFC_EINVAL
+    exp = ctx.expand(seeds)
+    with pytest.raises(AfcError):
+        ctx.sign_expanded_packed(exp, np.array([0, 1, 3], dtype=np.uint32), buf, good_off)          # index 3 of 3 keys
+    assert lib.afc_ed25519_verify_batch(H, None, None, _abi.ptr(buf), _abi.ptr(good_off), 3, None) == _abi.AFC_EINVAL
+    assert lib.afc_sha256_batch(None, _abi.ptr(buf), _abi.ptr(good_off), 3, _abi.ptr(out)) == _abi.AFC_EINVAL
+    assert (ctx.sha256_packed(buf, good_off) == CO.sha256_batch(buf, good_off)).all()              # and the context still works
+
+
 def test_ed25519_random_parity_ragged(ctx):
     rng = np.random.default_rng(0xAF02)
     n = 3000

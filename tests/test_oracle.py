@@ -170,3 +170,66 @@ def test_reference_flow_vectors():
     assert CO.sign(bytes.fromhex(vc["seed"]), msg).hex() == vc["sig"]
     assert CO.verify(bytes.fromhex(vc["pk"]), msg, bytes.fromhex(vc["sig"]))
     assert H.b64url_nopad(bytes.fromhex(vc["sig"])) == vc["proofValue"]
+
+
+def test_go_pinned_vectors_when_present():
+    """baseline/go/gen_golden_test.go, run where Go 1.24 and the reference exist, recomputes every expectation under tests/golden/
+    with the Go standard library and the reference's own structs and leaves tests/golden/go_pinned.json.  When that file is
+    present every value in it must equal the committed fixture (the Go run itself already fails on a difference); without it the
+    fixtures remain pinned to published vectors + two independent libraries only ("parity unpinned against Go")."""
+    import os
+    import pytest
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "go_pinned.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/go_pinned.json not present: no Go toolchain has re-pinned the fixtures yet")
+    pinned = golden("go_pinned.json")
+    assert pinned["failed"] is False, "the Go run reported mismatches"
+    got = {(e["File"], e["Case"], e["Field"]): e["Value"] for e in pinned["entries"]}
+    want = {}
+    for e in golden("rfc8032.json"):
+        want[("rfc8032.json", e["name"], "pk")] = e["pk"]; want[("rfc8032.json", e["name"], "sig")] = e["sig"]
+    for e in golden("ed25519_edge.json"):
+        want[("ed25519_edge.json", e["name"], "valid")] = "true" if e["valid"] else "false"
+    for e in golden("rfc4231.json"):
+        want[("rfc4231.json", e["name"], "tag")] = e["tag"]
+    g = golden("go_cases.json")
+    for c in g["floats"]:
+        want[("go_cases.json", "float " + c["bits"], "json")] = c["expect"]
+    for c in g["strings"]:
+        want[("go_cases.json", "string " + c["utf8"], "json")] = c["expect"]
+    for c in g["execution_vcs"]:
+        for f, k in (("canonical", "expect_canonical"), ("sig", "expect_sig"), ("stored", "expect_stored"), ("remarshalled", "expect_canonical")):
+            want[("go_cases.json", c["id"], f)] = c[k]
+    for c in g["workflow_vcs"]:
+        for f, k in (("canonical", "expect_canonical"), ("sig", "expect_sig"), ("stored", "expect_stored"), ("remarshalled", "expect_canonical")):
+            want[("go_cases.json", c["workflow_id"], f)] = c[k]
+    for c in g["webhooks"]:
+        want[("go_cases.json", c["execution_id"], "body")] = c["expect_body"]; want[("go_cases.json", c["execution_id"], "header")] = c["expect_header"]
+    flow = golden("reference_flow.json")
+    for d in flow["derivations"]:
+        for f in ("seed", "pk", "did"):
+            want[("reference_flow.json", d["path"], f)] = d[f]
+    missing = [k for k in want if k not in got]
+    assert not missing, missing[:5]
+    wrong = [(k, got[k], v) for k, v in want.items() if got[k] != v]
+    assert not wrong, wrong[:3]
+
+
+def test_go_cases_are_what_the_oracle_produces():
+    """tests/golden/go_cases.json is regenerated by tests/golden/make_golden.py from the oracle: check the committed file against
+    the oracle again (floats and strings in full, documents by signature), so the fixture cannot drift from its generator."""
+    import struct
+    from oracle import go_json as OJ, ref_vc as RV
+    g = golden("go_cases.json")
+    for c in g["floats"]:
+        assert OJ.number_bytes(struct.unpack(">d", bytes.fromhex(c["bits"]))[0]).decode() == c["expect"]
+    for c in g["strings"]:
+        assert (b'"' + OJ.escape_bytes(bytes.fromhex(c["utf8"])) + b'"').decode("utf-8") == c["expect"]
+    for c in g["execution_vcs"] + g["workflow_vcs"]:
+        msg, pk, sig = c["expect_canonical"].encode("utf-8"), bytes.fromhex(c["pk"]), bytes.fromhex(c["expect_sig"])
+        assert G.verify(pk, msg, sig) and CO.verify(pk, msg, sig) and CO.sign(bytes.fromhex(c["seed"]), msg) == sig
+    for c in g["workflow_vcs"]:
+        assert RV.verify_workflow_vc(c["expect_stored"].encode("utf-8"), bytes.fromhex(c["pk"]))
+    for c in g["webhooks"]:
+        assert H.webhook_signature(c["secret"], c["expect_body"].encode("utf-8")) == c["expect_header"]
