@@ -14,7 +14,8 @@ from .canonical import (JsonTemplate, vc_document_template, vc_document_values, 
                         workflow_vc_document_values)
 from .identity import ExpandedKeys, KeySet, did_key
 from .dispatcher import Ingest
+from .bundle import export_bundle, verify_bundle
 
 __all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "MerkleTree", "fold_roots", "verify_inclusion_batch", "verify_consistency_batch", "JsonTemplate", "vc_document_template", "vc_document_values", "workflow_vc_document_template", "workflow_vc_document_values",
-           "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key", "Ingest"]
+           "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key", "Ingest", "export_bundle", "verify_bundle"]
 __version__ = "0.1.0"

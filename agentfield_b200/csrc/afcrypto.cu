@@ -41,6 +41,10 @@ struct DevBuf {
         // zeroed once: the kernels read whole aligned words and mask what lies past a message, so the slack behind the last
         // staged byte is read (never used); this keeps those reads defined without a memset per call
         if (e == cudaSuccess) e = cudaMemset(p, 0, want);
+        // the memset runs on the legacy default stream and returns before it has happened; the buffer's users are NON-BLOCKING
+        // streams, which do not order themselves after it: without this wait a copy enqueued next could be zeroed afterwards
+        // (seen once as a wrong Merkle root right after a log was created)
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -203,6 +207,7 @@ const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
                   (ctx->kc_event || cudaEventCreateWithFlags(&ctx->kc_event, cudaEventDisableTiming) == cudaSuccess);
         cudaEvent_t* evs[] = {&k.ev_fork, &k.ev_join, &k.ev_plan, &k.ev_rows, &k.ev_chain[0], &k.ev_chain[1], &k.ev_chain[2], &k.ev_chain[3]};
         for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(cudaStreamLegacy) == cudaSuccess;        // the memsets above vs the non-blocking side streams
         if (!ok) { cudaGetLastError(); kc_free(ctx); ctx->kc_max_keys = 0; return nullptr; }     // no room: stay generic
         ctx->kc_ready = true;
     }
@@ -299,7 +304,7 @@ struct LaneDrain {
 
 int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
     if (A.n == 0) return AFC_OK;
-    if (!monotone(A.off, A.n) || (A.koff && !monotone(A.koff, A.n))) return AFC_EINVAL;
+    if (A.koff && !monotone(A.koff, A.n)) return AFC_EINVAL;
     CK(cudaSetDevice(ctx->device));
     LaneGuard lg(ctx);
     Lane& lane = lg.lane();
@@ -332,7 +337,12 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         uint32_t limit = left <= min_chunk ? left : (left + 1) / 2;
         if (limit < min_chunk) limit = min_chunk;
         if (limit > max_chunk) limit = max_chunk;
-        while (i1 < A.n && (i1 - i0) < limit && (A.off[i1 + 1] - base <= kChunkBytes || i1 == i0)) i1++;
+        // the walk that sizes the chunk also checks that the offsets never run backwards (no separate pass over n offsets)
+        while (i1 < A.n && (i1 - i0) < limit) {
+            if (A.off[i1 + 1] < A.off[i1]) return AFC_EINVAL;
+            if (A.off[i1 + 1] - base > kChunkBytes && i1 != i0) break;
+            i1++;
+        }
         uint32_t cnt = i1 - i0;
         uint64_t mbytes = A.off[i1] - base;
         Slot& sl = lane.slot[which];
@@ -862,6 +872,7 @@ int afc_merkle_new(afc_ctx* ctx, afc_merkle** out) {
     cudaError_t e = cudaMalloc((void**)&m->d_frontier, 64 * 32);
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_root, 32);
     if (e == cudaSuccess) e = cudaMemset(m->d_frontier, 0, 64 * 32);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);     // the log's own stream is non-blocking: it would not wait for that memset
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(m->ev, m->stream);

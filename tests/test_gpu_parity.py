@@ -529,6 +529,78 @@ def test_workflow_vc_issue_verify_and_comprehensive_audit(ctx):
     assert res["overall_score"] == max(0.0, ((100.0 - 25.0 * 5 - 5.0 * 2) + 60.0) / 2.0)
 
 
+def test_export_bundle_offline_audit(ctx):
+    """N4 end to end: issue a workflow of 300 credentials among 1 500 other log entries, export the bundle (EnhancedVCChain shape of
+    internal/cli/vc.go:78-97 + the audit_log section), verify it offline in three GPU batches — and see every kind of tampering
+    reported: an edited credential, a credential dropped from / never in the log, a forged tree head, a rewritten history."""
+    import copy
+    import json
+    from test_host_logic import _vc_requests
+    from agentfield_b200 import ExpandedKeys, export_bundle, verify_bundle
+    from agentfield_b200.services import VCService
+    from oracle import merkle as OM, go_hash as H
+    rng = np.random.default_rng(0xAF64)
+    master = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    cache = ExpandedKeys(ctx)
+    dids = cache.derive(master, ["m/44'/0'"] + ["m/44'/%d'/0'" % (3000 + a) for a in range(6)])
+    svc = VCService(cache, ctx)
+    reqs = _vc_requests(300, dids[1:], rng, pad_to=0)
+    for r in reqs:
+        r["workflow_id"], r["session_id"] = "wf-export", "sess-export"
+    issued = svc.generate_execution_vc_batch(reqs)
+    evs = [{"vc_id": r["vc_id"], "execution_id": r["execution_id"], "workflow_id": r["workflow_id"], "session_id": r["session_id"],
+            "issuer_did": r["caller_did"], "target_did": r.get("target_did", ""), "caller_did": r["caller_did"], "vc_document": v["vc_document"],
+            "signature": v["signature"], "input_hash": v["input_hash"], "output_hash": v["output_hash"], "status": r["status"],
+            "created_at": "2026-09-21T10:00:00Z"} for r, v in zip(reqs, issued)]
+    wfvc = svc.generate_workflow_vc_batch([{"workflow_id": "wf-export", "execution_vcs": evs, "root_did": dids[0], "vc_id": "vc-77", "workflow_vc_id": "vc-78",
+                                            "issuance_date": "2026-09-22T00:00:00Z", "snapshot_time": "2026-09-22T00:00:00Z",
+                                            "proof_created": "2026-09-22T00:00:01Z"}])[0]
+    # the audit log: 700 unrelated leaves, then this workflow's documents interleaved with 800 more
+    other = [rng.integers(0, 256, int(rng.integers(40, 400)), dtype=np.uint8).tobytes() for _ in range(1500)]
+    log, where = list(other[:700]), {}
+    for i, e in enumerate(evs):
+        where[e["vc_id"]] = len(log); log.append(e["vc_document"])
+        log += other[700 + 2 * i: 702 + 2 * i]
+    log += other[700 + 2 * len(evs):]
+    pks = {d: cache.public_key(d) for d in dids}
+    bundle = export_bundle("wf-export", evs, wfvc, pks, log, where, lambda m: cache.sign_batch([dids[0]], [m])[0], dids[0], "2026-09-22T01:00:00Z",
+                           checkpoints=(1, 700, 1000, len(log)), ctx=ctx)
+    # the exported head is the RFC 6962 root of the whole log (oracle), and the file survives a JSON round trip
+    sth = bundle["audit_log"]["signed_tree_head"]
+    assert sth["tree_size"] == len(log) and sth["root_hash"] == H.b64url_nopad(OM.root(log))
+    text = json.dumps(bundle)
+    res = verify_bundle(text, ctx)
+    assert res["valid"] and res["signature_valid"] and res["format_valid"] and res["type"] == "workflow", res.get("error")
+    assert res["summary"] == {"total_components": 300, "valid_components": 300, "total_dids": len(res["did_resolutions"]),
+                              "resolved_dids": len(res["did_resolutions"]), "total_signatures": 302, "valid_signatures": 302}
+    assert res["audit_log"]["included"] == 300 and res["audit_log"]["checkpoints_ok"] and len(res["audit_log"]["checkpoints"]) == 4
+    # a checkpoint root the auditor already trusts must match
+    trusted = {700: OM.root(log[:700])}
+    assert verify_bundle(text, ctx, trusted_checkpoints=trusted)["valid"]
+    assert not verify_bundle(text, ctx, trusted_checkpoints={700: OM.root(log[:699] + [b"x"])})["valid"]
+
+    def broken(mutate):
+        b = copy.deepcopy(bundle); mutate(b); return verify_bundle(json.dumps(b), ctx)
+    r1 = broken(lambda b: b["execution_vcs"][5]["vc_document"]["credentialSubject"]["execution"].__setitem__("durationMs", 123456789))
+    assert not r1["valid"] and not r1["component_results"][5]["signature_valid"] and r1["audit_log"]["not_included"] == [evs[5]["vc_id"]]
+    assert r1["summary"]["valid_signatures"] == 301 and r1["summary"]["valid_components"] == 299
+    r2 = broken(lambda b: b["audit_log"]["entries"][9]["inclusion_proof"].__setitem__(0, b["audit_log"]["entries"][10]["inclusion_proof"][0]))
+    assert not r2["valid"] and r2["audit_log"]["not_included"] == [evs[9]["vc_id"]] and r2["summary"]["valid_signatures"] == 302
+    r3 = broken(lambda b: b["audit_log"]["entries"].pop(0))
+    assert not r3["valid"] and r3["audit_log"]["not_included"] == [evs[0]["vc_id"]]
+    r4 = broken(lambda b: b["audit_log"]["signed_tree_head"].__setitem__("tree_size", len(log) - 1))
+    assert not r4["valid"] and not r4["audit_log"]["tree_head"]["signature_valid"]
+    r5 = broken(lambda b: b["audit_log"]["checkpoints"][1].__setitem__("root_hash", b["audit_log"]["checkpoints"][2]["root_hash"]))
+    assert not r5["valid"] and not r5["audit_log"]["checkpoints_ok"] and r5["summary"]["valid_signatures"] == 302
+    r6 = broken(lambda b: b["did_resolution_bundle"].pop(dids[2]))
+    assert not r6["valid"] and r6["summary"]["resolved_dids"] == r6["summary"]["total_dids"] - 1
+    r7 = broken(lambda b: b["execution_vcs"][3].__setitem__("execution_id", "exec-forged"))
+    assert not r7["valid"] and "Execution ID mismatch" in r7["component_results"][3]["error"]
+    r8 = broken(lambda b: b["workflow_vc"]["vc_document"]["credentialSubject"].__setitem__("totalSteps", 299))
+    assert not r8["valid"] and not r8["workflow_verification"]["signature_valid"]
+    assert not verify_bundle("{not json", ctx)["format_valid"] and not verify_bundle({"no": "workflow"}, ctx)["format_valid"]
+
+
 def test_ingest_dispatcher_results_and_audit_log(ctx):
     """N2 / configs[4] shape: actions submitted one by one come back with the oracle's signature and tag, and the dispatcher's
     audit log root is the RFC 6962 root over the signatures in ticket order, whatever the batch boundaries were."""
