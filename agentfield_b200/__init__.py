@@ -8,7 +8,7 @@ runs in libafcrypto.so on the GPU; there is no CPU fallback in this package (see
 """
 from . import _abi
 from ._abi import AfcError, LIB_PATH
-from .crypto import Context, Hasher, MAC, Signer, Verifier, default_context, pack, pack32
+from .crypto import Context, Hasher, MAC, PayloadHasher, Signer, Verifier, default_context, pack, pack32
 from .audit import Auditor, MerkleTree, fold_roots, verify_inclusion_batch, verify_consistency_batch
 from .canonical import (JsonTemplate, vc_document_template, vc_document_values, workflow_vc_document_template,
                         workflow_vc_document_values)
@@ -16,6 +16,6 @@ from .identity import ExpandedKeys, KeySet, did_key
 from .dispatcher import Ingest
 from .bundle import export_bundle, verify_bundle
 
-__all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "Signer", "Verifier", "Auditor", "MerkleTree", "fold_roots", "verify_inclusion_batch", "verify_consistency_batch", "JsonTemplate", "vc_document_template", "vc_document_values", "workflow_vc_document_template", "workflow_vc_document_values",
+__all__ = ["AfcError", "LIB_PATH", "Context", "Hasher", "MAC", "PayloadHasher", "Signer", "Verifier", "Auditor", "MerkleTree", "fold_roots", "verify_inclusion_batch", "verify_consistency_batch", "JsonTemplate", "vc_document_template", "vc_document_values", "workflow_vc_document_template", "workflow_vc_document_values",
            "default_context", "pack", "pack32", "ExpandedKeys", "KeySet", "did_key", "Ingest", "export_bundle", "verify_bundle"]
 __version__ = "0.1.0"

@@ -12,6 +12,7 @@ import numpy as np
 
 AFC_OK, AFC_EINVAL, AFC_ECUDA, AFC_ENOMEM, AFC_ENCCL, AFC_ESTATE = 0, -1, -2, -3, -4, -5
 MERKLE_STATE_BYTES = 8 + 64 * 32
+SHA256_STATE_BYTES = 108
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AFC_LIB", os.path.join(_HERE, "libafcrypto.so"))   # AFC_LIB: experiment builds only
@@ -36,6 +37,9 @@ SYMBOLS = {
     "afc_numa_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "afc_sha256_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
     "afc_sha256_batch_dev": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp]),
+    "afc_sha256_stream_init": (C.c_int, [vp, C.c_uint32]),
+    "afc_sha256_update_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp]),
+    "afc_sha256_update_batch_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp]),
     "afc_hmac_sha256_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp]),
     "afc_hmac_sha256_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_ed25519_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp]),
@@ -49,6 +53,8 @@ SYMBOLS = {
     "afc_ed25519_sign_expanded_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]),
     "afc_ed25519_sign_expanded_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp]),
     "afc_ed25519_sign_expanded_keys_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp]),
+    "afc_sign_configure": (C.c_int, [vp, C.c_int]),
+    "afc_sign_mode": (C.c_int, [vp]),
     "afc_keycache_configure": (C.c_int, [vp, C.c_uint32]),
     "afc_keycache_info": (C.c_int, [vp, u32p, u32p, u32p]),
     "afc_keycache_clear": (C.c_int, [vp, vp]),

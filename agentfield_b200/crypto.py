@@ -90,6 +90,13 @@ class Context:
         _abi.check(self._lib.afc_microbench(self.handle, which, iters, C.byref(ops), C.byref(ms)), self.handle)
         return ops.value, ms.value
 
+    def sign_configure(self, constant_time=True):
+        """Constant-time fixed-base multiplication for secret scalars (default) or the fast variable-time path."""
+        _abi.check(self._lib.afc_sign_configure(self.handle, 1 if constant_time else 0))
+
+    def sign_mode(self):
+        return "constant-time" if self._lib.afc_sign_mode(self.handle) == 1 else "fast"
+
     def keycache_configure(self, max_keys):
         """Capacity of the transparent issuer-key cache behind verify (0 disables it: always the generic kernel)."""
         _abi.check(self._lib.afc_keycache_configure(self.handle, int(max_keys)), self.handle)
@@ -230,6 +237,34 @@ class Hasher:
     def sha256_batch(self, msgs):
         buf, off = pack(msgs)
         return [bytes(r) for r in self.ctx.sha256_packed(buf, off)]
+
+
+class PayloadHasher:
+    """Streaming SHA-256 over many concurrent payload uploads: FilePayloadStore.SaveFromReader (internal/services/payload_store.go:45-97)
+    hashes each request / response payload while it streams to disk in 32 KiB chunks; here n streams advance together, one GPU
+    batch per round of chunks.  States are 108 bytes in Go's crypto/sha256 MarshalBinary layout (include/afcrypto.h)."""
+
+    def __init__(self, n_streams, ctx=None):
+        self.ctx = ctx or default_context()
+        self._lib = _abi.load()
+        self.states = np.zeros((n_streams, _abi.SHA256_STATE_BYTES), dtype=np.uint8)
+        _abi.check(self._lib.afc_sha256_stream_init(_abi.ptr(self.states), n_streams))
+
+    def update(self, chunks, final=None):
+        """chunks[i] (bytes, b"" for an idle stream) into stream i.  final: None, or a list of booleans — where set, the chunk may be
+        ragged and that stream's digest is returned (None elsewhere).  A non-final chunk must be a multiple of 64 bytes: ValueError."""
+        n = self.states.shape[0]
+        if len(chunks) != n:
+            raise ValueError("one chunk per stream")
+        fl = np.zeros(n, dtype=np.uint8) if final is None else np.array([1 if f else 0 for f in final], dtype=np.uint8)
+        for c, f in zip(chunks, fl):
+            if not f and len(c) % 64:
+                raise ValueError("only a stream's last chunk may have a length that is not a multiple of 64")
+        buf, off = pack([bytes(c) for c in chunks])
+        out = np.zeros((n, 32), dtype=np.uint8)
+        _abi.check(self._lib.afc_sha256_update_batch(self.ctx.handle, _abi.ptr(self.states), _abi.ptr(buf), _abi.ptr(off), n,
+                                                     _abi.ptr(fl) if final is not None else None, _abi.ptr(out)), self.ctx.handle)
+        return [bytes(out[i]) if fl[i] else None for i in range(n)]
 
 
 class MAC:

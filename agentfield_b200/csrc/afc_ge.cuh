@@ -244,6 +244,52 @@ AFC_HD void ge_scalarmult_base(ge_p3& h, const uint32_t* a, const ge_precomp* ba
     }
 }
 
+// ---- constant-time fixed-base multiplication, for SECRET scalars (signing nonces r and private scalars s) --------------------
+// ge_scalarmult_base above gathers table entries at addresses made of the scalar's digits and skips zero digits: fine for
+// public scalars (verification), a cache/timing side channel for secret ones — Go's crypto/ed25519, which signing replaces
+// (vc_service.go:460-463), selects table entries in constant time.  The constant-time path: signed radix 16, 64 rows of 8
+// multiples (48 KB, staged in shared memory by the kernels), EVERY entry of a row read for every digit and one kept by mask,
+// no branch and no address that depends on the scalar; a zero digit adds the neutral element.
+//   ct16[i][j] = (j+1) 16^i B — all 512 entries already exist in the radix-65536 table: base[i/4][16^(i%4) (j+1) - 1].
+static constexpr int CT_ROWS = 64, CT_COLS = 8;
+AFC_HD size_t ge_ct16_source(int i, int j) { return (size_t)(i >> 2) * BASE_COLS + (((size_t)(j + 1)) << (4 * (i & 3))) - 1; }
+AFC_HD void ge_ct_select(ge_precomp& e, const ge_precomp* row, int d) {
+    const uint32_t neg = (uint32_t)(d >> 31);                              // all ones iff d < 0
+    const uint32_t m = ((uint32_t)d ^ neg) - neg;                          // |d| in 0..8
+    fe_1(e.ypx); fe_1(e.ymx); fe_0(e.xy2d);                                // d = 0: the neutral element in precomputed form
+#pragma unroll
+    for (int j = 0; j < CT_COLS; j++) {
+        const uint32_t mask = 0u - (uint32_t)(m == (uint32_t)(j + 1));
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            e.ypx.v[w] ^= (e.ypx.v[w] ^ row[j].ypx.v[w]) & mask;
+            e.ymx.v[w] ^= (e.ymx.v[w] ^ row[j].ymx.v[w]) & mask;
+            e.xy2d.v[w] ^= (e.xy2d.v[w] ^ row[j].xy2d.v[w]) & mask;
+        }
+    }
+    fe nx; fe_neg(nx, e.xy2d);
+#pragma unroll
+    for (int w = 0; w < 8; w++) {                                          // -P: swap y+x and y-x, negate 2dxy
+        const uint32_t t = (e.ypx.v[w] ^ e.ymx.v[w]) & neg;
+        e.ypx.v[w] ^= t; e.ymx.v[w] ^= t;
+        e.xy2d.v[w] ^= (e.xy2d.v[w] ^ nx.v[w]) & neg;
+    }
+}
+template <class F = FeInline>
+AFC_HD void ge_scalarmult_base_ct(ge_p3& h, const uint32_t* a, const ge_precomp* ct16) {
+    uint32_t t[8];
+    sc_recode16(t, a);                                                     // 64 signed digits in [-8, 7]
+    ge_p3_0(h);
+#pragma unroll 1
+    for (int i = 0; i < CT_ROWS; i++) {
+        ge_precomp e;
+        ge_ct_select(e, ct16 + i * CT_COLS, sc_digit16(t, i));
+        ge_p1p1 r;
+        ge_maddsub<F>(r, h, e, 0);
+        ge_p1p1_to_p3<F>(h, r);
+    }
+}
+
 // Canonical encodings of G projective points with ONE field inversion (Montgomery's trick).  Every Z must be non-zero
 // (true for any point on the curve: the a = -1 twisted Edwards addition law is complete).
 template <class F, int G>

@@ -99,7 +99,7 @@ int process(afc_ingest* g, Batch& B) {
     cp(B.d_msgs, B.h_msgs, B.msg_bytes); cp(B.d_moff, B.h_moff, (size_t)(n + 1) * 8); cp(B.d_ki, B.h_ki, (size_t)n * 4);
     cp(B.d_keys, B.h_keys, B.key_bytes); cp(B.d_koff, B.h_koff, (size_t)(n + 1) * 4);
     cp(B.d_bodies, B.h_bodies, B.body_bytes); cp(B.d_boff, B.h_boff, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = launch::ed_sign_expanded_batch(afc_internal_comb(g->ctx), g->d_expanded, g->n_keys, B.d_ki, B.d_msgs, B.d_moff, n, B.d_sigs, st, &lg);
+    if (e == cudaSuccess) e = launch::ed_sign_expanded_batch(afc_internal_comb(g->ctx), afc_internal_sign_table(g->ctx), g->d_expanded, g->n_keys, B.d_ki, B.d_msgs, B.d_moff, n, B.d_sigs, st, &lg);
     if (e == cudaSuccess) e = launch::hmac_sha256_batch(B.d_keys, B.d_koff, B.d_bodies, B.d_boff, n, B.d_tags, st, &lg);
     afc_internal_add_launches(g->ctx, lg.n);
     if (e != cudaSuccess) return AFC_ECUDA;

@@ -41,6 +41,9 @@ struct LaunchLog {
 cudaError_t sha256_batch(const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg);
 cudaError_t hmac_sha256_batch(const uint8_t* keys, const uint32_t* koff, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                               uint8_t* out32, cudaStream_t s, LaunchLog* lg);
+// streaming SHA-256: 108-byte states (Go MarshalBinary layout) in/out, chunk i into state i, digest where final_flags[i]
+cudaError_t sha256_update(uint8_t* states, const uint8_t* chunks, const uint64_t* off, uint32_t n, const uint8_t* final_flags, uint8_t* out32,
+                          uint8_t* status, cudaStream_t s, LaunchLog* lg);
 cudaError_t merkle_leaf_hashes(const uint8_t* leaves, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg);
 // One tree level.  in: node array whose element 0 has level-index s_idx; npairs pairs starting at element `first`
 // (first = 1 when s_idx was odd and the left orphan in[0] merges with frontier[h]); out[carry..] receives the parents.
@@ -125,13 +128,16 @@ cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs,
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                                   uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
-cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+// ct16: the 48 KB constant-time table (ed_build_ct_table) or nullptr for the fast, variable-time fixed-base multiplication
+size_t ed_ct_table_bytes();
+cudaError_t ed_build_ct_table(const void* comb, void* ct16, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_sign_batch(const void* comb, const void* ct16, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                           uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
 // n_keys bounds key_index on the device (an index >= n_keys signs with key 0 instead of reading out of bounds; the host entry
 // point has already rejected such a batch, the device-pointer one cannot look)
-cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index, const uint8_t* msgs,
-                                   const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
-cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
+cudaError_t ed_sign_expanded_batch(const void* comb, const void* ct16, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index,
+                                   const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg);
+cudaError_t ed_expand_batch(const void* comb, const void* ct16, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
                             cudaStream_t s, LaunchLog* lg);
 // returns number of mismatches in *d_mismatch (device uint32)
 cudaError_t ed_selftest(uint32_t iters, uint32_t* d_mismatch, cudaStream_t s, LaunchLog* lg);

@@ -124,6 +124,52 @@ AFC_HD void sha256_finish_stream(uint32_t st[8], const uint8_t* msg, uint64_t le
     }
 }
 
+// Absorb whole blocks only (len % 64 == 0), no padding: the middle of a stream (FilePayloadStore.SaveFromReader feeds the hash
+// 32 KiB at a time, payload_store.go:69-94,154).
+AFC_HD void sha256_absorb_blocks(uint32_t st[8], const uint8_t* msg, uint64_t len) {
+    uint64_t nfull = len >> 6;
+    if ((((uintptr_t)msg) & 15) == 0) {
+        for (uint64_t blk = 0; blk < nfull; blk++) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                word4 v = ld_u128(msg + 16 * q);
+                w[4 * q] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+            }
+            sha256_compress(st, w);
+            msg += 64;
+        }
+        return;
+    }
+    PadStream ps; ps.init(msg, nfull << 6);
+    for (uint64_t blk = 0; blk < nfull; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = ps.next_be();
+        sha256_compress(st, w);
+    }
+}
+// Streaming state between calls, laid out exactly like Go's crypto/sha256 (*digest).MarshalBinary: "sha\x03" || h[0..7] big-endian ||
+// 64-byte block buffer || total length big-endian = 108 bytes.  States handed across this boundary always sit on a block
+// boundary (length % 64 == 0), so the buffer is all zeros; a Go caller can UnmarshalBinary such a state and continue, and back.
+static constexpr int SHA256_STATE_BYTES = 108;
+AFC_HD int sha256_state_load(uint32_t st[8], uint64_t* total, const uint8_t* s) {
+    if (s[0] != 's' || s[1] != 'h' || s[2] != 'a' || s[3] != 3) return 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ((uint32_t)s[4 + 4 * i] << 24) | ((uint32_t)s[5 + 4 * i] << 16) | ((uint32_t)s[6 + 4 * i] << 8) | s[7 + 4 * i];
+    uint64_t t = 0;
+    for (int i = 0; i < 8; i++) t = (t << 8) | s[100 + i];
+    *total = t;
+    return (t & 63) == 0;
+}
+AFC_HD void sha256_state_store(uint8_t* s, const uint32_t st[8], uint64_t total) {
+    s[0] = 's'; s[1] = 'h'; s[2] = 'a'; s[3] = 3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) store_be32(s + 4 + 4 * i, st[i]);
+    for (int i = 0; i < 64; i++) s[36 + i] = 0;
+    for (int i = 0; i < 8; i++) s[100 + i] = (uint8_t)(total >> (56 - 8 * i));
+}
+
 AFC_HD void sha256_msg(uint32_t st[8], const uint8_t* msg, uint64_t len) {
     sha256_init(st);
     sha256_finish_stream(st, msg, len, 0);

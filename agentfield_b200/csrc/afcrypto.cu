@@ -83,6 +83,8 @@ struct afc_ctx {
     int device = 0;
     cudaDeviceProp prop{};
     void* comb = nullptr;
+    void* ct16 = nullptr;               // 48 KB constant-time signing table (radix 16), gathered from comb at init
+    bool sign_ct = true;                // secret scalars go through the constant-time fixed-base multiplication (AFC_SIGN_CT=0: fast path)
     Lane lanes[kLanes];
     std::mutex mu;
     std::condition_variable cv;
@@ -325,6 +327,7 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         Slot& sl = lane.slot[w];
         CK(cudaStreamSynchronize(sl.stream));
         if (!pin_out) memcpy(A.out + (size_t)pend[w].i0 * A.out_item, sl.h_out.p, (size_t)pend[w].cnt * A.out_item);
+        if (A.op == OP_SIGN && !pin_a && sl.h_in.p) memset(sl.h_in.p, 0, sl.h_in.cap);         // nor in the pinned bounce buffer
         pend[w].active = false;
         return AFC_OK;
     };
@@ -400,15 +403,16 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
                                               (const uint32_t*)sl.koff.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
             break;
         }
-        case OP_SIGN: e = launch::ed_sign_batch(ctx->comb, sl.a.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
+        case OP_SIGN: e = launch::ed_sign_batch(ctx->comb, afc_internal_sign_table(ctx), sl.a.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
         case OP_SIGN_EXP: {
             const uint32_t* d_ki = nullptr;
             if (A.key_index) { CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used)); d_ki = (const uint32_t*)sl.koff.p; }
-            e = launch::ed_sign_expanded_batch(ctx->comb, A.d_expanded + (A.key_index ? 0 : (size_t)i0 * 96), 0xffffffffu, d_ki, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
+            e = launch::ed_sign_expanded_batch(ctx->comb, afc_internal_sign_table(ctx), A.d_expanded + (A.key_index ? 0 : (size_t)i0 * 96), 0xffffffffu, d_ki, d_base, d_off, cnt, sl.out.p, sl.stream, lc);
             break;
         }
         }
         CK(e);
+        if (A.op == OP_SIGN) CK(cudaMemsetAsync(sl.a.p, 0, (size_t)cnt * A.a_item, sl.stream));   // seeds do not stay behind in the staging slot
         CK(cudaMemcpyAsync(pin_out ? A.out + (size_t)i0 * A.out_item : sl.h_out.p, sl.out.p, (size_t)cnt * A.out_item,
                            cudaMemcpyDeviceToHost, sl.stream));
         pend[which] = {i0, cnt, true};
@@ -470,6 +474,7 @@ static void numa_discover(afc_ctx* ctx) {
 
 int afc_internal_device(afc_ctx* ctx) { return ctx->device; }
 const void* afc_internal_comb(afc_ctx* ctx) { return ctx->comb; }
+const void* afc_internal_sign_table(afc_ctx* ctx) { return ctx->sign_ct ? ctx->ct16 : nullptr; }
 void afc_internal_add_launches(afc_ctx* ctx, unsigned long long n) { ctx->launches += n; }
 
 extern "C" {
@@ -519,9 +524,12 @@ int afc_init(int device, afc_ctx** out) {
             if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&ctx->comb, launch::ed_tables_bytes())) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
     cudaStream_t s0 = ctx->lanes[0].slot[0].stream;
+    if ((e = cudaMalloc(&ctx->ct16, launch::ed_ct_table_bytes())) != cudaSuccess) return fail(e, "cudaMalloc(ct table)");
+    if (const char* ev = getenv("AFC_SIGN_CT")) ctx->sign_ct = atoi(ev) != 0;
     {   // the launch log must be gone before fail() can destroy the context it points into
         CallLog lc(ctx);
         e = launch::ed_build_tables(ctx->comb, s0, lc);
+        if (e == cudaSuccess) e = launch::ed_build_ct_table(ctx->comb, ctx->ct16, s0, lc);
     }
     if (e != cudaSuccess) return fail(e, "ed_build_tables");
     if ((e = cudaStreamSynchronize(s0)) != cudaSuccess) return fail(e, "ed_build_tables sync");
@@ -543,6 +551,7 @@ void afc_destroy(afc_ctx* ctx) {
     kc_free(ctx);
     if (ctx->kc_event) cudaEventDestroy(ctx->kc_event);
     if (ctx->comb) cudaFree(ctx->comb);
+    if (ctx->ct16) cudaFree(ctx->ct16);
     for (auto& r : ctx->prof_recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
     delete ctx;
 }
@@ -554,6 +563,13 @@ int afc_device_info(afc_ctx* ctx, int* sm_count, int* clock_khz, uint64_t* mem_b
     if (mem_bytes) *mem_bytes = ctx->prop.totalGlobalMem;
     return AFC_OK;
 }
+
+int afc_sign_configure(afc_ctx* ctx, int constant_time) {
+    if (!ctx) return AFC_EINVAL;
+    ctx->sign_ct = constant_time != 0;
+    return AFC_OK;
+}
+int afc_sign_mode(afc_ctx* ctx) { return ctx ? (ctx->sign_ct ? 1 : 0) : AFC_EINVAL; }
 
 uint64_t afc_launch_count(afc_ctx* ctx) { return ctx ? (uint64_t)ctx->launches.load() : 0; }
 
@@ -596,6 +612,70 @@ int afc_ed25519_sign_batch(afc_ctx* ctx, const uint8_t* seeds, const uint8_t* ms
     return run_host_batch(ctx, A);
 }
 
+// ---------------------------------------------------------------------------------- H2: streaming SHA-256
+int afc_sha256_stream_init(uint8_t* states, uint32_t n) {
+    if (!states && n) return AFC_EINVAL;
+    static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t* s = states + (size_t)AFC_SHA256_STATE_BYTES * i;
+        memset(s, 0, AFC_SHA256_STATE_BYTES);
+        s[0] = 's'; s[1] = 'h'; s[2] = 'a'; s[3] = 3;
+        for (int w = 0; w < 8; w++) { s[4 + 4 * w] = (uint8_t)(iv[w] >> 24); s[5 + 4 * w] = (uint8_t)(iv[w] >> 16); s[6 + 4 * w] = (uint8_t)(iv[w] >> 8); s[7 + 4 * w] = (uint8_t)iv[w]; }
+    }
+    return AFC_OK;
+}
+int afc_sha256_update_batch(afc_ctx* ctx, uint8_t* states, const uint8_t* chunks, const uint64_t* chunk_off, uint32_t n, const uint8_t* final_flags,
+                            uint8_t* out32) {
+    if (!ctx || !chunk_off || (n && !states)) return AFC_EINVAL;
+    if (n == 0) return AFC_OK;
+    bool any_final = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if (chunk_off[i + 1] < chunk_off[i]) return AFC_EINVAL;
+        const bool fin = final_flags && final_flags[i];
+        any_final |= fin;
+        if (!fin && ((chunk_off[i + 1] - chunk_off[i]) & 63)) return AFC_EINVAL;      // only a stream's last chunk may be ragged
+    }
+    if (any_final && !out32) return AFC_EINVAL;
+    const uint64_t base = chunk_off[0], bytes = chunk_off[n] - base;
+    if (bytes && !chunks) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    LaneGuard lg(ctx);
+    Slot& sl = lg.lane().slot[0];
+    LaneDrain drain_on_exit(lg.lane());
+    const size_t pad = (size_t)(base & 15);
+    CK(sl.msgs.reserve(bytes + 32)); CK(sl.off.reserve((size_t)(n + 1) * 8)); CK(sl.a.reserve((size_t)n * AFC_SHA256_STATE_BYTES));
+    CK(sl.b.reserve((size_t)n * 2 + 16)); CK(sl.out.reserve((size_t)n * 32 + 16));
+    if (bytes) CK(cudaMemcpyAsync(sl.msgs.p + pad, chunks + base, bytes, cudaMemcpyHostToDevice, sl.stream));
+    CK(cudaMemcpyAsync(sl.off.p, chunk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(cudaMemcpyAsync(sl.a.p, states, (size_t)n * AFC_SHA256_STATE_BYTES, cudaMemcpyHostToDevice, sl.stream));
+    uint8_t* d_fin = nullptr;
+    if (final_flags) { d_fin = sl.b.p; CK(cudaMemcpyAsync(d_fin, final_flags, n, cudaMemcpyHostToDevice, sl.stream)); }
+    uint8_t* d_status = sl.b.p + n;
+    {
+        CallLog lc(ctx);
+        CK(launch::sha256_update(sl.a.p, sl.msgs.p + pad - base, (const uint64_t*)sl.off.p, n, d_fin, sl.out.p, d_status, sl.stream, lc));
+    }
+    std::vector<uint8_t> status(n), dig(any_final ? (size_t)n * 32 : 0);
+    CK(cudaMemcpyAsync(states, sl.a.p, (size_t)n * AFC_SHA256_STATE_BYTES, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(status.data(), d_status, n, cudaMemcpyDeviceToHost, sl.stream));
+    if (any_final) CK(cudaMemcpyAsync(dig.data(), sl.out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    drain_on_exit.armed = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!status[i]) return AFC_EINVAL;                                             // a state that is not ours (or not on a block boundary)
+        if (final_flags && final_flags[i]) memcpy(out32 + 32ull * i, dig.data() + 32ull * i, 32);
+    }
+    return AFC_OK;
+}
+int afc_sha256_update_batch_dev(afc_ctx* ctx, uint8_t* d_states, const uint8_t* d_chunks, const uint64_t* d_chunk_off, uint32_t n,
+                                const uint8_t* d_final_flags, uint8_t* d_out32, uint8_t* d_status, void* stream) {
+    if (!ctx) return AFC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CallLog lc(ctx);
+    CK(launch::sha256_update(d_states, d_chunks, d_chunk_off, n, d_final_flags, d_out32, d_status, (cudaStream_t)stream, lc));
+    return AFC_OK;
+}
+
 static int expand_common(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t* out, size_t item, bool expanded) {
     if (!ctx || (n && (!seeds || !out))) return AFC_EINVAL;
     if (n == 0) return AFC_OK;
@@ -605,8 +685,10 @@ static int expand_common(afc_ctx* ctx, const uint8_t* seeds, uint32_t n, uint8_t
     CK(sl.a.reserve((size_t)n * 32)); CK(sl.out.reserve((size_t)n * item));
     CK(cudaMemcpyAsync(sl.a.p, seeds, (size_t)n * 32, cudaMemcpyHostToDevice, sl.stream));
     CallLog lc(ctx);
-    CK(launch::ed_expand_batch(ctx->comb, sl.a.p, n, expanded ? sl.out.p : nullptr, expanded ? nullptr : sl.out.p, sl.stream, lc));
+    CK(launch::ed_expand_batch(ctx->comb, afc_internal_sign_table(ctx), sl.a.p, n, expanded ? sl.out.p : nullptr, expanded ? nullptr : sl.out.p, sl.stream, lc));
     CK(cudaMemcpyAsync(out, sl.out.p, (size_t)n * item, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemsetAsync(sl.a.p, 0, (size_t)n * 32, sl.stream));                       // seeds and expanded private keys are wiped from the slot
+    if (expanded) CK(cudaMemsetAsync(sl.out.p, 0, (size_t)n * item, sl.stream));
     CK(cudaStreamSynchronize(sl.stream));
     return AFC_OK;
 }
@@ -670,19 +752,19 @@ int afc_ed25519_sign_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, const uint8
                                uint32_t n, uint8_t* d_sigs, void* stream) {
     DEV_PROLOGUE();
     if (!aligned16(d_seeds) || !aligned16(d_sigs)) return AFC_EINVAL;
-    CK(launch::ed_sign_batch(ctx->comb, d_seeds, d_msgs, d_msg_off, n, d_sigs, st, lc));
+    CK(launch::ed_sign_batch(ctx->comb, afc_internal_sign_table(ctx), d_seeds, d_msgs, d_msg_off, n, d_sigs, st, lc));
     DEV_EPILOGUE();
 }
 int afc_ed25519_pubkey_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_pks, void* stream) {
     DEV_PROLOGUE();
     if (!aligned16(d_seeds) || !aligned16(d_pks)) return AFC_EINVAL;
-    CK(launch::ed_expand_batch(ctx->comb, d_seeds, n, nullptr, d_pks, st, lc));
+    CK(launch::ed_expand_batch(ctx->comb, afc_internal_sign_table(ctx), d_seeds, n, nullptr, d_pks, st, lc));
     DEV_EPILOGUE();
 }
 int afc_ed25519_expand_batch_dev(afc_ctx* ctx, const uint8_t* d_seeds, uint32_t n, uint8_t* d_expanded96, void* stream) {
     DEV_PROLOGUE();
     if (!aligned16(d_seeds) || !aligned16(d_expanded96)) return AFC_EINVAL;
-    CK(launch::ed_expand_batch(ctx->comb, d_seeds, n, d_expanded96, nullptr, st, lc));
+    CK(launch::ed_expand_batch(ctx->comb, afc_internal_sign_table(ctx), d_seeds, n, d_expanded96, nullptr, st, lc));
     DEV_EPILOGUE();
 }
 int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, const uint32_t* d_key_index,
@@ -693,7 +775,7 @@ int afc_ed25519_sign_expanded_keys_batch_dev(afc_ctx* ctx, const uint8_t* d_expa
                                              const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream) {
     DEV_PROLOGUE();
     if (!aligned16(d_expanded96) || !aligned16(d_sigs) || n_keys == 0) return AFC_EINVAL;
-    CK(launch::ed_sign_expanded_batch(ctx->comb, d_expanded96, n_keys, d_key_index, d_msgs, d_msg_off, n, d_sigs, st, lc));
+    CK(launch::ed_sign_expanded_batch(ctx->comb, afc_internal_sign_table(ctx), d_expanded96, n_keys, d_key_index, d_msgs, d_msg_off, n, d_sigs, st, lc));
     DEV_EPILOGUE();
 }
 int afc_merkle_leaf_hashes_dev(afc_ctx* ctx, const uint8_t* d_leaves, const uint64_t* d_leaf_off, uint32_t n, uint8_t* d_out32, void* stream) {

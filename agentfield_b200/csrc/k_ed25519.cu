@@ -38,6 +38,13 @@ k_ed_build_tables(ge_precomp* base) {
     if (t < BASE_ROWS * CPR) ge_build_base_chunk<FeCall>(base + (size_t)t * BASE_CHUNK, t / CPR, (t % CPR) * BASE_CHUNK);
 }
 
+// the 512 entries of the constant-time signing table, copied out of the radix-65536 table (afc_init, once per context)
+__global__ void __launch_bounds__(256)
+k_ed_build_ct16(const ge_precomp* __restrict__ base, ge_precomp* __restrict__ ct16) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < CT_ROWS * CT_COLS) ct16[t] = base[ge_ct16_source(t / CT_COLS, t % CT_COLS)];
+}
+
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
           const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out) {
@@ -569,9 +576,26 @@ k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const ui
 // are computed first and encoded with ONE field inversion (Montgomery's trick): per credential the inversion was 70 % of the
 // field work of a signature from an expanded key (16 mixed additions = 112 multiplications against 265) and twice that from a seed.
 constexpr int SIGN_GMAX = 8;
+// CT = true: `comb` is the 48 KB constant-time table (ge_scalarmult_base_ct), staged in shared memory; every scalar that is
+// multiplied here is secret (the nonce r, and the private scalar s when signing from seeds).
+template <bool CT>
+__device__ __forceinline__ const ge_precomp* stage_ct_table(const ge_precomp* comb) {
+    if (!CT) return comb;
+    extern __shared__ uint4 s_ct_raw[];
+    const uint4* src = (const uint4*)comb;
+    for (int i = threadIdx.x; i < (int)(sizeof(ge_precomp) * CT_ROWS * CT_COLS / 16); i += blockDim.x) s_ct_raw[i] = __ldg(src + i);
+    __syncthreads();
+    return (const ge_precomp*)s_ct_raw;
+}
+template <bool CT, class F>
+__device__ __forceinline__ void base_mult(ge_p3& h, const uint32_t* a, const ge_precomp* tab) {
+    if (CT) ge_scalarmult_base_ct<F>(h, a, tab); else ge_scalarmult_base<F>(h, a, tab);
+}
+template <bool CT>
 __global__ void __launch_bounds__(ED_THREADS)
-k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, uint32_t n_keys,
+k_ed_sign(const ge_precomp* __restrict__ comb_in, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ key_index, uint32_t n_keys,
           const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ sigs) {
+    const ge_precomp* comb = stage_ct_table<CT>(comb_in);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int mode = n_keys != 0;                                 // n_keys = 0: `keys` are seeds, one per credential
@@ -589,7 +613,7 @@ k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys,
             ed25519_expand_scalar(sc[g], prefix, seed);
             sc_reduce256(sr, sc[g]);
             ge_p3 A;
-            ge_scalarmult_base<FeCall>(A, sr, comb);
+            base_mult<CT, FeCall>(A, sr, comb);
             fe_copy(X[G + g], A.X); fe_copy(Y[G + g], A.Y); fe_copy(Z[G + g], A.Z);
         } else {
             uint32_t kidx = key_index ? key_index[i] : (uint32_t)i;
@@ -600,7 +624,7 @@ k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys,
         const uint64_t o0 = off[i], o1 = off[i + 1];
         ed25519_nonce(rr[g], prefix, msgs + o0, o1 - o0);
         ge_p3 R;
-        ge_scalarmult_base<FeCall>(R, rr[g], comb);
+        base_mult<CT, FeCall>(R, rr[g], comb);
         fe_copy(X[g], R.X); fe_copy(Y[g], R.Y); fe_copy(Z[g], R.Z);
     }
     uint32_t enc[2 * SIGN_GMAX][8];
@@ -618,9 +642,11 @@ k_ed_sign(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ keys,
 }
 
 // seeds -> expanded96 (s || prefix || pk) and/or pks (32 B each); G seeds per thread share one inversion, as in k_ed_sign
+template <bool CT>
 __global__ void __launch_bounds__(ED_THREADS)
-k_ed_expand(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ seeds, uint32_t n, uint32_t T, int G,
+k_ed_expand(const ge_precomp* __restrict__ comb_in, const uint8_t* __restrict__ seeds, uint32_t n, uint32_t T, int G,
             uint8_t* __restrict__ expanded96, uint8_t* __restrict__ pks) {
+    const ge_precomp* comb = stage_ct_table<CT>(comb_in);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     fe X[SIGN_GMAX], Y[SIGN_GMAX], Z[SIGN_GMAX];
@@ -635,7 +661,7 @@ k_ed_expand(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ see
         ed25519_expand_scalar(sc[g], pre[g], seed);
         sc_reduce256(sr, sc[g]);
         ge_p3 A;
-        ge_scalarmult_base<FeCall>(A, sr, comb);
+        base_mult<CT, FeCall>(A, sr, comb);
         fe_copy(X[g], A.X); fe_copy(Y[g], A.Y); fe_copy(Z[g], A.Z);
     }
     uint32_t enc[SIGN_GMAX][8];
@@ -830,8 +856,11 @@ static int pick_group(uint32_t n, const void* kernel) {          // table-driven
                           "AFC_KC_GROUP");
 }
 // signing / key expansion: 16 mixed additions + two (one) SHA-512 passes worth ~240 (~60) multiplications of time
-static int pick_sign_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_sign, 2, 362, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
-static int pick_expand_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_expand, 3, 180, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
+static int pick_sign_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_sign<false>, 2, 362, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
+static int pick_expand_group(uint32_t n) { return pick_group_for(n, (const void*)k_ed_expand<false>, 3, 180, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
+// constant-time signing: 64 mixed additions + masked table scans instead of 16 additions (occupancy taken from the fast kernel's
+// register count: the shared-memory table allows 4 CTAs per SM, which the registers do not exceed)
+static int pick_sign_group_ct(uint32_t n) { return pick_group_for(n, (const void*)k_ed_sign<false>, 2, 362 + 48 * 7 + 200, 270, SIGN_GMAX, "AFC_SIGN_GROUP"); }
 
 cudaError_t ed_keycache_clear(const KeyCache& kc, cudaStream_t s, LaunchLog* lg) {
     const uint64_t cnt = (uint64_t)kc.slot_mask + 1;
@@ -953,28 +982,40 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
     AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, T, G, ok));
     return cudaGetLastError();
 }
-cudaError_t ed_sign_batch(const void* comb, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+// ct16 != nullptr selects the constant-time kernels (48 KB of dynamic shared memory for the table)
+constexpr size_t CT_SMEM = sizeof(ge_precomp) * CT_ROWS * CT_COLS;
+size_t ed_ct_table_bytes() { return CT_SMEM; }
+cudaError_t ed_build_ct_table(const void* comb, void* ct16, cudaStream_t s, LaunchLog* lg) {
+    static_assert(BASE_W == 16, "the constant-time table is gathered from the radix-65536 table");
+    AFC_LAUNCH(lg, "k_ed_build_ct16", s, k_ed_build_ct16<<<blocks_for(CT_ROWS * CT_COLS, 256), 256, 0, s>>>((const ge_precomp*)comb, (ge_precomp*)ct16));
+    return cudaGetLastError();
+}
+static void launch_sign(const void* comb, const void* ct16, const uint8_t* keys, const uint32_t* key_index, uint32_t n_keys, const uint8_t* msgs,
+                        const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
+    const int G = ct16 ? pick_sign_group_ct(n) : pick_sign_group(n);
+    const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
+    if (ct16) AFC_LAUNCH(lg, "k_ed_sign_ct", s, k_ed_sign<true><<<blocks_for(T, ED_THREADS), ED_THREADS, CT_SMEM, s>>>((const ge_precomp*)ct16, keys, key_index, n_keys, msgs, off, n, T, G, sigs));
+    else AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<false><<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, keys, key_index, n_keys, msgs, off, n, T, G, sigs));
+}
+cudaError_t ed_sign_batch(const void* comb, const void* ct16, const uint8_t* seeds, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                           uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
-    const int G = pick_sign_group(n);
-    const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, nullptr, 0u, msgs, off, n, T, G, sigs));
+    launch_sign(comb, ct16, seeds, nullptr, 0u, msgs, off, n, sigs, s, lg);
     return cudaGetLastError();
 }
-cudaError_t ed_sign_expanded_batch(const void* comb, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index, const uint8_t* msgs,
-                                   const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
+cudaError_t ed_sign_expanded_batch(const void* comb, const void* ct16, const uint8_t* expanded96, uint32_t n_keys, const uint32_t* key_index,
+                                   const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* sigs, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
-    const int G = pick_sign_group(n);
-    const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_sign", s, k_ed_sign<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, expanded96, key_index, n_keys, msgs, off, n, T, G, sigs));
+    launch_sign(comb, ct16, expanded96, key_index, n_keys, msgs, off, n, sigs, s, lg);
     return cudaGetLastError();
 }
-cudaError_t ed_expand_batch(const void* comb, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
+cudaError_t ed_expand_batch(const void* comb, const void* ct16, const uint8_t* seeds, uint32_t n, uint8_t* expanded96, uint8_t* pks_only,
                             cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     const int G = pick_expand_group(n);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_expand", s, k_ed_expand<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, n, T, G, expanded96, pks_only));
+    if (ct16) AFC_LAUNCH(lg, "k_ed_expand_ct", s, k_ed_expand<true><<<blocks_for(T, ED_THREADS), ED_THREADS, CT_SMEM, s>>>((const ge_precomp*)ct16, seeds, n, T, G, expanded96, pks_only));
+    else AFC_LAUNCH(lg, "k_ed_expand", s, k_ed_expand<false><<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, seeds, n, T, G, expanded96, pks_only));
     return cudaGetLastError();
 }
 cudaError_t ed_selftest(uint32_t iters, uint32_t* d_mismatch, cudaStream_t s, LaunchLog* lg) {

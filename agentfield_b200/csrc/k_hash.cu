@@ -29,6 +29,31 @@ k_sha256_batch(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ of
     store_digest256(out + 32ull * i, st);
 }
 
+// H2 streaming (FilePayloadStore.SaveFromReader, internal/services/payload_store.go:45-97): stream i absorbs chunk i into its
+// 108-byte state; where final[i] is set the chunk may be ragged, the stream is padded and out32[i] receives the digest (the state
+// is left as it was after the last whole block: a finished stream is not resumed).  status[i] = 0 for a malformed state.
+__global__ void __launch_bounds__(HASH_THREADS)
+k_sha256_update(uint8_t* __restrict__ states, const uint8_t* __restrict__ chunks, const uint64_t* __restrict__ off, uint32_t n,
+                const uint8_t* __restrict__ final_flags, uint8_t* __restrict__ out32, uint8_t* __restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t* s = states + (size_t)SHA256_STATE_BYTES * i;
+    uint32_t st[8];
+    uint64_t prior;
+    const int ok = sha256_state_load(st, &prior, s);
+    const uint64_t o0 = off[i], len = off[i + 1] - o0;
+    const bool fin = final_flags && final_flags[i];
+    if (!ok || (!fin && (len & 63))) { if (status) status[i] = 0; return; }
+    if (status) status[i] = 1;
+    if (!fin) {
+        sha256_absorb_blocks(st, chunks + o0, len);
+        sha256_state_store(s, st, prior + len);
+    } else {
+        sha256_finish_stream(st, chunks + o0, len, prior);
+        for (int w = 0; w < 8; w++) store_be32(out32 + 32ull * i + 4 * w, st[w]);
+    }
+}
+
 __global__ void __launch_bounds__(HASH_THREADS)
 k_hmac_sha256_batch(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ koff, const uint8_t* __restrict__ msgs,
                     const uint64_t* __restrict__ off, uint32_t n, uint8_t* __restrict__ out) {
@@ -389,6 +414,12 @@ static inline uint32_t blocks_for(uint64_t n, int t) { return (uint32_t)((n + t 
 cudaError_t sha256_batch(const uint8_t* msgs, const uint64_t* off, uint32_t n, uint8_t* out32, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     AFC_LAUNCH(lg, "k_sha256_batch", s, k_sha256_batch<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(msgs, off, n, out32));
+    return cudaGetLastError();
+}
+cudaError_t sha256_update(uint8_t* states, const uint8_t* chunks, const uint64_t* off, uint32_t n, const uint8_t* final_flags, uint8_t* out32,
+                          uint8_t* status, cudaStream_t s, LaunchLog* lg) {
+    if (n == 0) return cudaSuccess;
+    AFC_LAUNCH(lg, "k_sha256_update", s, k_sha256_update<<<blocks_for(n, HASH_THREADS), HASH_THREADS, 0, s>>>(states, chunks, off, n, final_flags, out32, status));
     return cudaGetLastError();
 }
 cudaError_t hmac_sha256_batch(const uint8_t* keys, const uint32_t* koff, const uint8_t* msgs, const uint64_t* off, uint32_t n,

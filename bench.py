@@ -382,13 +382,32 @@ def cfg4_block(ctx, dev, rank, world, barrier, reps=3):
         times.append(float(t.item()))
     ms = min(times)
     root = bytes(groot.cpu().tolist())
+    # the same with the other fixed-base multiplication for the nonces (default: constant time; the fast path gathers from the
+    # radix-65536 table at addresses made of nonce digits) — same signatures, same root
+    mode = ctx.sign_mode()
+    ctx.sign_configure(mode != "constant-time")
+    once(); torch.cuda.synchronize()
+    other = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(); once(); e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        other.append(float(t.item()))
+    other_same_root = bytes(groot.cpu().tolist()) == root
+    ctx.sign_configure(mode == "constant-time")
     # every rank must hold the same global root
     same = True
     if world > 1:
         r0 = groot.clone(); dist.broadcast(r0, 0)
         flag = torch.tensor([int(torch.equal(r0, groot))], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         same = bool(flag.item())
-    blk = {"leaves_total": n_total, "leaves_per_gpu": per, "ms": ms, "signs_plus_appends_per_s": n_total / (ms * 1e-3), "root": root.hex(),
+    blk = {"leaves_total": n_total, "leaves_per_gpu": per, "sign_mode": mode, "ms": ms, "signs_plus_appends_per_s": n_total / (ms * 1e-3),
+           ("fast_variable_time_ms" if mode == "constant-time" else "constant_time_ms"): min(other), "other_mode_same_root": other_same_root,
+           "root": root.hex(),
            "same_root_on_every_rank": same,
            "collective": "ncclAllGather of %d x 32 B subtree roots (torch.distributed, NCCL over NVLink)" % world if world > 1
            else "none (single GPU: the fold of one root)", "hbm_frac": 640.0 * per / (ms * 1e-3) / 1e9 / peaks()[0]}
@@ -482,9 +501,14 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank)           # before torch / CUDA allocate anything pinned
     # NCCL's own init lines (ranks, transports) go to stderr so that a reader of the run can see how many ranks joined;
     # stdout carries the one JSON line only
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("AFC_NCCL_DEBUG", "INFO"))
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    nccl_log = None
+    if world > 1:
+        # (NCCL writes its debug lines to STDOUT unless told otherwise, and /dev/stderr as NCCL_DEBUG_FILE was ignored on the pool's
+        # boxes: each rank logs to a file of its own and copies it to stderr once the communicator is up)
+        nccl_log = "/tmp/afc_nccl_rank%d_%d.log" % (rank, os.getpid())
+        os.environ["NCCL_DEBUG"] = os.environ.get("AFC_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("AFC_NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
     import torch
     import torch.distributed as dist
     import agentfield_b200 as afb
@@ -505,6 +529,17 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if world > 1:
+        barrier()                                      # the first collective creates the communicator: its init lines are in the log now
+        try:
+            with open(nccl_log) as f:
+                for ln in f:
+                    if rank == 0 or "Init COMPLETE" in ln or "nranks" in ln.lower():
+                        sys.stderr.write(ln)
+            sys.stderr.flush()
+        except OSError as ex:
+            sys.stderr.write("bench.py: NCCL log %s not readable: %r\n" % (nccl_log, ex))
 
     if args.soak > 0:
         soak(args, ctx, dev, rank, world, barrier, numa)

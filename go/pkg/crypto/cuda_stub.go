@@ -4,7 +4,8 @@ package crypto
 
 import "errors"
 
-// NewCUDA is unavailable in builds without `-tags cuda` + cgo; callers keep the stdlib backend.
-func NewCUDA(devices []int) (Backend, error) {
+// openCUDA is unavailable in builds without `-tags cuda` + cgo (the reference's CI matrix builds with CGO_ENABLED=0,
+// .github/workflows/control-plane.yml:79): asking for backend "cuda" in such a build is a start-up error, not a silent fallback.
+func openCUDA(devices []int, signConstantTime bool, keyCacheMaxKeys int) (Backend, error) {
 	return nil, errors.New("crypto: built without the cuda backend (need CGO_ENABLED=1 and -tags cuda)")
 }

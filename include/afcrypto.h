@@ -68,6 +68,19 @@ int afc_sha256_batch(afc_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets,
 int afc_sha256_batch_dev(afc_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, uint32_t n,
                          uint8_t* d_out32, void* stream);
 
+/* H2 streaming: FilePayloadStore.SaveFromReader (internal/services/payload_store.go:45-97) hashes a payload while it streams to
+ * disk, 32 KiB at a time (:154).  Many concurrent uploads = many streams advancing together: stream i absorbs chunk i into its
+ * state.  A state is 108 bytes laid out like Go's crypto/sha256 (*digest).MarshalBinary ("sha\x03" || h big-endian || 64-byte
+ * buffer || length big-endian) and always sits on a block boundary, so Go code can UnmarshalBinary it and carry on, and back.
+ * Every chunk except a stream's last must be a multiple of 64 bytes (the reference's 32 KiB are); where final_flags[i] != 0 the
+ * chunk may have any length (also 0), the digest goes to out32[i] and the state is finished.  final_flags may be NULL (none). */
+#define AFC_SHA256_STATE_BYTES 108
+int afc_sha256_stream_init(uint8_t* states /* n x 108 */, uint32_t n);
+int afc_sha256_update_batch(afc_ctx* ctx, uint8_t* states /* n x 108, in/out */, const uint8_t* chunks, const uint64_t* chunk_off /* n+1 */,
+                            uint32_t n, const uint8_t* final_flags /* n or NULL */, uint8_t* out32 /* n x 32, written where final */);
+int afc_sha256_update_batch_dev(afc_ctx* ctx, uint8_t* d_states, const uint8_t* d_chunks, const uint64_t* d_chunk_off, uint32_t n,
+                                const uint8_t* d_final_flags, uint8_t* d_out32, uint8_t* d_status /* n: 0 = malformed state */, void* stream);
+
 /* ---- W1: HMAC-SHA256 ----------------------------------------------------------------------------
  * replaces generateWebhookSignature (internal/services/webhook_dispatcher.go:470-474): tag =
  * HMAC-SHA256(key = secret bytes, msg = body); the "sha256="+hex header text stays host-side.
@@ -153,6 +166,15 @@ int afc_ed25519_sign_expanded_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded9
  * the host-buffer call rejects such a batch with AFC_EINVAL, a device-side index array cannot be inspected without a sync) */
 int afc_ed25519_sign_expanded_keys_batch_dev(afc_ctx* ctx, const uint8_t* d_expanded96, uint32_t n_keys, const uint32_t* d_key_index,
                                              const uint8_t* d_msgs, const uint64_t* d_msg_off, uint32_t n, uint8_t* d_sigs, void* stream);
+
+/* Secret scalars (the signing nonce r, and the private scalar when keys are expanded) are multiplied in CONSTANT TIME by default,
+ * as Go's crypto/ed25519 does: signed radix 16, a 48 KB table staged in shared memory, every entry of a row read for every digit
+ * and one kept by mask — no branch and no address depends on key material.  afc_sign_configure(ctx, 0) (or AFC_SIGN_CT=0) selects
+ * the fast variable-time path (radix-65536 table gathers: 16 additions instead of 64) for deployments where nothing untrusted
+ * shares the GPU.  Results are identical either way.  Seeds and expanded keys staged by the host-buffer calls are wiped from the
+ * device slot and the pinned bounce buffer when the call completes.  afc_sign_mode: 1 = constant time. */
+int afc_sign_configure(afc_ctx* ctx, int constant_time);
+int afc_sign_mode(afc_ctx* ctx);
 
 /* ---- M1: RFC 6962 Merkle audit log (NEW — the reference's chain check is a stub,
  * internal/cli/vc_verification_enhanced.go:531-534; nearest code generateWorkflowVCDocument,

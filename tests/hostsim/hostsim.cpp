@@ -99,6 +99,31 @@ int hs_key_row_mismatches(const uint8_t pk[32], int i) {
     }
     return bad;
 }
+// constant-time fixed-base multiplication (masked scan of the 48 KB radix-16 table gathered from the radix-65536 table, as
+// k_ed_build_ct16 does) against the variable-time one: words in which the canonical encodings of [a]B differ
+int hs_scalarmult_ct_mismatches(const uint8_t scalar[32]) {
+    ensure_tables();
+    static std::vector<ge_precomp> ct;
+    if (ct.empty()) { ct.resize(CT_ROWS * CT_COLS); for (int t = 0; t < CT_ROWS * CT_COLS; t++) ct[t] = g_comb[ge_ct16_source(t / CT_COLS, t % CT_COLS)]; }
+    uint32_t a[8], r[8]; words_from_bytes(a, scalar, 8);
+    sc_reduce256(r, a);
+    ge_p3 h1, h2;
+    ge_scalarmult_base(h1, r, &g_comb[0]);
+    ge_scalarmult_base_ct(h2, r, &ct[0]);
+    uint32_t e1[8], e2[8];
+    ge_encode(e1, h1.X, h1.Y, h1.Z); ge_encode(e2, h2.X, h2.Y, h2.Z);
+    int bad = 0;
+    for (int w = 0; w < 8; w++) bad += e1[w] != e2[w];
+    return bad;
+}
+// what one thread of k_sha256_update does: absorb a chunk into a 108-byte state (Go MarshalBinary layout) or finish the stream
+int hs_sha256_stream_update(uint8_t* state, const uint8_t* chunk, uint64_t len, int fin, uint8_t out32[32]) {
+    uint32_t st[8]; uint64_t prior;
+    if (!sha256_state_load(st, &prior, state) || (!fin && (len & 63))) return 0;
+    if (!fin) { sha256_absorb_blocks(st, chunk, len); sha256_state_store(state, st, prior + len); }
+    else { sha256_finish_stream(st, chunk, len, prior); for (int w = 0; w < 8; w++) store_be32(out32 + 4 * w, st[w]); }
+    return 1;
+}
 // The round-2 construction (k_kc_chain + k_kc_rows): the chain in `stages` stages leaving P, 32 P, 64 P per row, slices started
 // from those helpers, forward run / inversion / backward run — against the single-thread form.  The CTA-wide product tree that
 // shares the inversion on the device is replaced here by one inversion per slice (same values); returns mismatching words.

@@ -64,3 +64,32 @@ def test_kernels_are_sm100a_sass():
     so = os.path.join(ROOT, "agentfield_b200", "libafcrypto.so")
     out = subprocess.check_output(["cuobjdump", "-lelf", so]).decode()
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def _build_c_harness():
+    import subprocess
+    d = os.path.join(ROOT, "tests", "c_abi")
+    subprocess.check_call(["make", "-s", "-C", d])
+    return os.path.join(d, "harness")
+
+
+def test_plain_c_caller_compiles_and_fails_loudly_without_a_gpu():
+    """tests/c_abi/harness.c is what a cgo binding amounts to: a C99 translation unit that sees only include/afcrypto.h and links
+    libafcrypto.so.  It must build with -Wall -Wextra -pedantic, and on a box without a GPU report AFC_ECUDA (exit code 77) instead
+    of computing anything on the CPU."""
+    import subprocess
+    import torch
+    exe = _build_c_harness()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the harness is run by the gpu-marked test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 77 and "no CPU path" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_passes_its_known_answer_checks():
+    """The same program on the GPU box: RFC 8032 TEST 1-3 (sign, public key, verify, a corrupted signature reported as ok = 0),
+    RFC 4231 case 2, SHA-256 one-shot and streaming, the first Certificate-Transparency roots — through the C ABI from C."""
+    import subprocess
+    r = subprocess.run([_build_c_harness()], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "c_abi harness ok" in r.stdout, (r.returncode, r.stdout, r.stderr)

@@ -128,6 +128,46 @@ def test_sha256_hmac_ragged_lengths_and_alignments(ctx):
     assert tags[6].tobytes() == hmac.new(keys[6], msgs[6], hashlib.sha256).digest()
 
 
+def test_streaming_sha256_payload_hasher(ctx):
+    """H2 (FilePayloadStore.SaveFromReader, payload_store.go:45-97): 24 concurrent streams of 0 B ... 64 MiB advance 32 KiB at a
+    time (plus ragged final chunks) through afc_sha256_update_batch; every digest equals hashlib's over the whole stream, states
+    survive a save / restore between rounds, and a malformed state or a ragged middle chunk is refused."""
+    import hashlib
+    from agentfield_b200 import AfcError, PayloadHasher, _abi
+    rng = np.random.default_rng(0xAF69)
+    sizes = [0, 1, 63, 64, 65, 32767, 32768, 32769, 100_000, 1_000_000, 5_000_000, 64 << 20] + [int(x) for x in rng.integers(1, 300_000, 12)]
+    datas = [rng.integers(0, 256, s_, dtype=np.uint8).tobytes() if s_ < (8 << 20) else (rng.integers(0, 256, 1 << 20, dtype=np.uint8).tobytes() * (s_ >> 20))
+             for s_ in sizes]
+    ph = PayloadHasher(len(datas), ctx)
+    pos, done, digests = [0] * len(datas), [False] * len(datas), [None] * len(datas)
+    CH = 32 * 1024                                              # the reference's copy buffer (payload_store.go:154)
+    rounds = 0
+    while not all(done):
+        chunks, final = [], []
+        for i, d in enumerate(datas):
+            if done[i]:
+                chunks.append(b""); final.append(False); continue
+            step = CH * (64 if len(d) > (8 << 20) else 1)       # the 64 MiB stream moves 2 MiB per round to keep the test short
+            if len(d) - pos[i] > step:
+                chunks.append(d[pos[i]:pos[i] + step]); final.append(False); pos[i] += step
+            else:
+                chunks.append(d[pos[i]:]); final.append(True); pos[i] = len(d)
+        out = ph.update(chunks, final)
+        for i, f in enumerate(final):
+            if f:
+                digests[i], done[i] = out[i], True
+        rounds += 1
+        if rounds == 3:                                         # states are plain bytes: persist and restore between rounds
+            saved = ph.states.copy(); ph = PayloadHasher(len(datas), ctx); ph.states[:] = saved
+    assert [d.hex() for d in digests] == [hashlib.sha256(d).hexdigest() for d in datas]
+    ph = PayloadHasher(2, ctx)
+    with pytest.raises(ValueError):
+        ph.update([b"x" * 65, b""])
+    ph.states[1, 0] = 0                                         # not a state any more
+    with pytest.raises(AfcError):
+        ph.update([b"", b""], [True, True])
+
+
 def test_empty_batches(ctx):
     from agentfield_b200 import Auditor
     z8, off0 = np.zeros(1, np.uint8), np.zeros(1, np.uint64)
@@ -186,6 +226,35 @@ def test_ed25519_random_parity_ragged(ctx):
     exp = CO.ed25519_verify_batch(p2, s2, b2, off, 8)
     assert (ok == exp).all()
     assert 0.55 * n < ok.sum() < 0.7 * n
+
+
+def test_constant_time_and_fast_signing_agree_with_the_oracle(ctx):
+    """E1: the default constant-time fixed-base multiplication (k_ed_sign_ct / k_ed_expand_ct) and the fast gather path produce the
+    same signatures and public keys — RFC 8032's and the oracle's — from seeds and from expanded keys, ragged messages."""
+    rng = np.random.default_rng(0xAF71)
+    n = 3000
+    seeds = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    lens = rng.integers(0, 700, n)
+    off = np.zeros(n + 1, dtype=np.uint64); off[1:] = np.cumsum(lens)
+    buf = rng.integers(0, 256, int(off[-1]) + 1, dtype=np.uint8)
+    want = CO.ed25519_sign_batch(seeds, buf, off, 8)
+    want_pk = CO.ed25519_pubkey_batch(seeds, 8)
+    assert ctx.sign_mode() == "constant-time"                      # the default
+    try:
+        for ct in (True, False):
+            ctx.sign_configure(ct)
+            assert (ctx.sign_packed(seeds, buf, off) == want).all(), ct
+            assert (ctx.pubkeys(seeds) == want_pk).all(), ct
+            exp = ctx.expand(seeds[:64])
+            assert (exp[:, 64:] == want_pk[:64]).all()
+            ki = rng.integers(0, 64, n).astype(np.uint32)
+            assert (ctx.sign_expanded_packed(exp, ki, buf, off) == CO.ed25519_sign_batch(seeds[ki].copy(), buf, off, 8)).all(), ct
+        g = golden("rfc8032.json")
+        from agentfield_b200 import Signer
+        ctx.sign_configure(True)
+        assert [s_.hex() for s_ in Signer(ctx).sign_batch([bytes.fromhex(e["seed"]) for e in g], [bytes.fromhex(e["msg"]) for e in g])] == [e["sig"] for e in g]
+    finally:
+        ctx.sign_configure(True)
 
 
 def test_expanded_key_cache_sign(ctx):

@@ -206,3 +206,69 @@ def test_go_json_escaping_and_template_fill(hostsim):
         out = np.zeros(n + 4, dtype=np.uint8)
         hostsim.hs_json_fill_one(*args, out.ctypes.data_as(C.c_void_p))
         assert out[:n].tobytes() == want
+
+
+def _py_sha256_compress(h, block):
+    """FIPS 180-4 §6.2.2 in plain Python: the independent check of the chaining values inside a streaming state."""
+    K = [0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3,
+         0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+         0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,
+         0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+         0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+         0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2]
+    M = 0xffffffff
+    r = lambda x, n: ((x >> n) | (x << (32 - n))) & M
+    w = [int.from_bytes(block[4 * i:4 * i + 4], "big") for i in range(16)]
+    for i in range(16, 64):
+        s0 = r(w[i - 15], 7) ^ r(w[i - 15], 18) ^ (w[i - 15] >> 3); s1 = r(w[i - 2], 17) ^ r(w[i - 2], 19) ^ (w[i - 2] >> 10)
+        w.append((w[i - 16] + s0 + w[i - 7] + s1) & M)
+    a, b, c, d, e, f, g, hh = h
+    for i in range(64):
+        t1 = (hh + (r(e, 6) ^ r(e, 11) ^ r(e, 25)) + ((e & f) ^ (~e & g & M)) + K[i] + w[i]) & M
+        t2 = ((r(a, 2) ^ r(a, 13) ^ r(a, 22)) + ((a & b) ^ (a & c) ^ (b & c))) & M
+        hh, g, f, e, d, c, b, a = g, f, e, (d + t1) & M, c, b, a, (t1 + t2) & M
+    return [(x + y) & M for x, y in zip(h, (a, b, c, d, e, f, g, hh))]
+
+
+def test_streaming_sha256_state_is_go_marshal_binary_layout(hostsim):
+    """H2 (payload_store.go:69-94): chunked absorption == hashlib over the whole stream for random chunkings and alignments, and the
+    108-byte state between chunks is "sha\\x03" || h big-endian || 64 zero bytes || length big-endian — crypto/sha256's MarshalBinary
+    form for a digest sitting on a block boundary — with h checked by an independent FIPS 180-4 compression."""
+    import ctypes as C
+    import hashlib
+    rng = np.random.default_rng(0xAF68)
+    iv = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+    for trial in range(60):
+        total = int(rng.integers(0, 5000))
+        data = rng.integers(0, 256, total + 16, dtype=np.uint8).tobytes()
+        shift = int(rng.integers(0, 16))                              # chunk pointers at every alignment
+        data = data[shift:shift + total]
+        state = (C.c_uint8 * 108)(*(b"sha\x03" + b"".join(x.to_bytes(4, "big") for x in iv) + bytes(64) + bytes(8)))
+        out = (C.c_uint8 * 32)()
+        pos, h = 0, list(iv)
+        while total - pos >= 64 and rng.random() < 0.8:
+            k = 64 * int(rng.integers(1, max(2, (total - pos) // 64 + 1)))
+            chunk = data[pos:pos + k]
+            assert hostsim.hs_sha256_stream_update(state, chunk, len(chunk), 0, out) == 1
+            for b in range(0, k, 64):
+                h = _py_sha256_compress(h, chunk[b:b + 64])
+            pos += k
+            assert bytes(state) == b"sha\x03" + b"".join(x.to_bytes(4, "big") for x in h) + bytes(64) + pos.to_bytes(8, "big")
+        assert hostsim.hs_sha256_stream_update(state, data[pos:], total - pos, 1, out) == 1
+        assert bytes(out) == hashlib.sha256(data).digest(), (trial, total, pos)
+    bad = (C.c_uint8 * 108)(*bytes(108))
+    assert hostsim.hs_sha256_stream_update(bad, b"", 0, 1, out) == 0                     # not a state
+    ok = (C.c_uint8 * 108)(*(b"sha\x03" + b"".join(x.to_bytes(4, "big") for x in iv) + bytes(72)))
+    assert hostsim.hs_sha256_stream_update(ok, b"x" * 65, 65, 0, out) == 0              # ragged chunk in the middle of a stream
+
+
+def test_constant_time_base_multiplication_equals_variable_time(hostsim):
+    """ge_scalarmult_base_ct (signed radix 16, masked scans, neutral element for zero digits, conditional negation) computes the
+    same point as the radix-65536 gather path — for random scalars and for the digit patterns that exercise every branch-free
+    case: zero, all digits 0x8 (-8 everywhere), all 0x7, all 0xf, a single top digit, L - 1."""
+    rng = np.random.default_rng(0xAF70)
+    cases = [bytes(32), bytes([0x88] * 32), bytes([0x77] * 32), bytes([0xff] * 32), bytes(31) + b"\x0f", b"\x01" + bytes(31),
+             (2**252 + 27742317777372353535851937790883648493 - 1).to_bytes(32, "little")]
+    cases += [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(40)]
+    for c in cases:
+        assert hostsim.hs_scalarmult_ct_mismatches(c) == 0, c.hex()
