@@ -99,9 +99,10 @@ def generate_webhook_signature_batch(secrets, bodies, ctx=None):
 class VCService:
     """Batched issue / verify of execution VCs over a key cache (DID -> expanded key) and an issuer key set."""
 
-    def __init__(self, keys: ExpandedKeys, ctx=None, hash_sensitive_data=True, canonical_on_device=False):
+    def __init__(self, keys: ExpandedKeys, ctx=None, hash_sensitive_data=True, canonical_on_device=False, store=None):
         self.ctx = ctx or keys.ctx
         self.keys = keys
+        self.store = store                                        # vc_store.ExecutionVCStore: the issued batch is persisted in ONE transaction
         self.hash_sensitive_data = hash_sensitive_data
         self.canonical_on_device = canonical_on_device
         self._templates = None
@@ -166,6 +167,12 @@ class VCService:
             out.append({"vc_document": vc_bytes, "signature": proof["proofValue"],
                         "input_hash": doc["credentialSubject"]["execution"]["inputHash"],
                         "output_hash": doc["credentialSubject"]["execution"]["outputHash"], "doc": doc, "proof": proof})
+        if self.store is not None and out:                        # vc_service.go:229-233, for the whole batch at once (group commit)
+            self.store.store_execution_vcs([
+                {"vc_id": r["vc_id"], "execution_id": r["execution_id"], "workflow_id": r["workflow_id"], "session_id": r["session_id"],
+                 "issuer_did": r["caller_did"], "target_did": r.get("target_did", ""), "caller_did": r["caller_did"], "vc_document": v["vc_document"],
+                 "signature": v["signature"], "input_hash": v["input_hash"], "output_hash": v["output_hash"],
+                 "status": normalize_execution_status(r["status"])} for r, v in zip(requests, out)])
         return out
 
     # -- E2 / D1

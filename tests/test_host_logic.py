@@ -247,3 +247,43 @@ def test_workflow_status_roll_up_and_normalisation():
         assert S.determine_workflow_status(evs) == RV.determine_workflow_status([S.normalize_execution_status(e["status"]) for e in evs])
         assert S.count_completed_steps(evs) == sum(e["status"] in ("succeeded", "completed") for e in evs)
     assert S.determine_workflow_status([]) == "pending"
+
+
+def test_group_commit_persistence(tmp_path):
+    """N2: the reference commits one credential at a time (StoreExecutionVC, internal/storage/local.go:6336-6361); the batch seam
+    commits a batch at a time.  Same table, same UPSERT, same rows either way; a re-issued vc_id replaces document / signature /
+    status and nothing else; a batch is atomic; and on a real file with synchronous=FULL the group commit is many times faster."""
+    import time
+    from agentfield_b200.vc_store import ExecutionVCStore
+    rng = np.random.default_rng(9)
+
+    def vc(i, wf="wf-1", doc=None):
+        return {"vc_id": "vc-%06d" % i, "execution_id": "exec-%06d" % i, "workflow_id": wf, "session_id": "s", "issuer_did": "did:key:zA",
+                "target_did": "did:key:zB", "caller_did": "did:key:zA", "vc_document": doc or ('{"n":%d,"pad":"%s"}' % (i, "x" * 1200)).encode(),
+                "signature": "sig-%d" % i, "input_hash": "ih", "output_hash": "oh", "status": "succeeded"}
+    a, b = ExecutionVCStore(str(tmp_path / "one.db")), ExecutionVCStore(str(tmp_path / "batch.db"))
+    n = 400
+    vcs = [vc(i) for i in range(n)]
+    t0 = time.perf_counter()
+    for v in vcs:
+        a.store_execution_vc(v)
+    t_one = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b.store_execution_vcs(vcs)
+    t_batch = time.perf_counter() - t0
+    assert a.count() == b.count() == n and a.commits == n and b.commits == 1
+    ra, rb = a.get_execution_vc("vc-000123"), b.get_execution_vc("vc-000123")
+    assert {k: v for k, v in ra.items() if k != "created_at"} == {k: v for k, v in rb.items() if k != "created_at"}
+    assert rb["document_size_bytes"] == len(vcs[123]["vc_document"]) and [r["vc_id"] for r in b.workflow_vcs("wf-1")][:3] == ["vc-000000", "vc-000001", "vc-000002"]
+    assert t_batch < t_one / 5, (t_one, t_batch)               # one journal sync instead of 400
+    # UPSERT: document, signature, status, size are replaced; ids and hashes of the first insert stay
+    again = dict(vc(123), vc_document=b'{"changed":true}', signature="sig-new", status="failed", input_hash="OTHER")
+    b.store_execution_vcs([again])
+    r2 = b.get_execution_vc("vc-000123")
+    assert (r2["vc_document"], r2["signature"], r2["status"], r2["document_size_bytes"], r2["input_hash"]) == ('{"changed":true}', "sig-new", "failed", 16, "ih")
+    # atomic: a batch with a row that violates the (execution_id, issuer, target) uniqueness leaves nothing behind
+    clash = dict(vc(900), execution_id="exec-000005")           # another vc_id for an execution that already has one
+    with pytest.raises(Exception):
+        b.store_execution_vcs([vc(901), clash, vc(902)])
+    assert b.count() == n and b.get_execution_vc("vc-000901") is None
+    a.close(); b.close()

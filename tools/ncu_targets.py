@@ -40,13 +40,16 @@ d_voff = torch.arange(ns * tmpl.n_fields + 1, device=dev, dtype=torch.int64) * 3
 def one_pass():
     tmpl.fill_dev(d_vals, d_voff, ns)                                 # k_json_sizes, k_scan_*, k_json_fill
     ctx.keycache_clear()
-    ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)            # cold: k_kc_bases, k_kc_build, k_ed_hram, k_ed_verify_cached
+    ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)            # cold: k_kc_dedup ... k_kc_chain4, k_kc_rows, k_kc_scatter, k_ed_hram, k_ed_verify_cached
     ks.verify_dev(d_ki, d_sigs, d_msgs, d_off, n, d_ok)               # k_ed_hram_keyed, k_ed_verify_keyed
     ctx.hmac_sha256_dev(keys.view(-1), koff, bodies.view(-1), boff, m, tags)
     ctx.sha256_dev(bodies.view(-1), boff, m, tags)
-    ctx.expand_dev(kseeds, bench.N_KEYS, d_exp)
+    ctx.expand_dev(kseeds, bench.N_KEYS, d_exp)                      # constant-time (default): k_ed_expand_ct, k_ed_sign_ct
     ctx.sign_expanded_dev(d_exp, ski, d_msgs, d_off, ns, sigs2)
     ctx.sign_dev(seeds_full, d_msgs, d_off, ns, sigs2)
+    ctx.sign_configure(False)                                         # fast variable-time path: k_ed_sign
+    ctx.sign_expanded_dev(d_exp, ski, d_msgs, d_off, ns, sigs2)
+    ctx.sign_configure(True)
     a = afb.Auditor(ctx)
     a.append_dev(sigs2.view(-1), soff, ns)
     a.root_dev(root)
