@@ -78,6 +78,7 @@ def bind_to_gpu_numa_node(index):
     info = {"bound": False}
     try:
         allowed = os.sched_getaffinity(0)
+        bind_to_gpu_numa_node.original = set(allowed)
         cpus = None
         try:
             import pynvml
@@ -103,6 +104,16 @@ def bind_to_gpu_numa_node(index):
     except Exception as ex:
         info["error"] = repr(ex)
     return info
+
+
+def unbind_for_cpu_legs():
+    """The CPU baselines use every host thread the process may use: undo the NUMA binding of the GPU sections first."""
+    orig = getattr(bind_to_gpu_numa_node, "original", None)
+    if orig:
+        try:
+            os.sched_setaffinity(0, orig)
+        except OSError:
+            pass
 
 
 def peaks():
@@ -748,6 +759,7 @@ def main():
             torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        unbind_for_cpu_legs()
         line["cpu_baseline"] = cpu_baseline_block(host_threads(), 12.0)
     if args.extras:
         line["extras"] = extras(ctx, dev, world, rank)
@@ -796,6 +808,7 @@ def soak(args, ctx, dev, rank, world, barrier, numa):
             "collective": "ncclAllGather of the %d per-rank audit roots" % world if world > 1 else "none",
             "pushed": {"target_rate_per_gpu": 1_000_000, "achieved_rate": float(summed[6]), "p99_us_max_over_ranks": float(maxed[7])}, "numa": numa}
     if not args.no_cpu_baseline:
+        unbind_for_cpu_legs()
         line["cpu_baseline"] = cpu_ingest_rate(host_threads())
     print(json.dumps(line), flush=True)
 

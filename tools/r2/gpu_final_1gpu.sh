@@ -25,5 +25,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^
 timeout 1800 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"^k_(ed_|hmac|sha256|merkle_leaf|merkle_level|kc_|json)" -c 90 -o $out/prof_all -f python tools/ncu_targets.py > $out/ncu_all.log 2>&1
 tail -2 $out/ncu_all.log
 ncu -i $out/prof_all.ncu-rep --page raw --csv > $out/prof_all_raw.csv 2>/dev/null
-ncu -i $out/prof_all.ncu-rep --page source --csv --kernel-name regex:k_ed_verify_cached --print-source sass > $out/verify_cached_source.csv 2>/dev/null
+ncu -i $out/prof_all.ncu-rep --page source --csv --kernel-name regex:k_ed_verify_cached --print-source sass > /tmp/verify_cached_source.csv 2>/dev/null
+python tools/ncu_stalls.py /tmp/verify_cached_source.csv > $out/verify_cached_stalls.txt 2>&1
+python tools/ncu_summary.py $out/prof_all_raw.csv > $out/ncu_all_kernels_summary.txt 2>&1
+rm -f $out/prof_all.ncu-rep        # 120 MB: gpurun_out/ is capped at 64 MiB
 ls -la $out/
