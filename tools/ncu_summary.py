@@ -27,7 +27,10 @@ def main():
         col.setdefault(h, i)
     out = {}
     for r in rows[2:]:
-        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        full = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
+        name = full.split("<")[0]
+        if name in ("k_ed_sign", "k_ed_expand") and "<1>" in full:      # template <bool CT>: the constant-time instantiation
+            name += "_ct"
         print(name)
         rec = {}
         for w in WANT:
