@@ -191,8 +191,39 @@ AFC_HD void fe_dbl(fe& h, const fe& f) { fe_add(h, f, f); }
 
 // ---------------------------------------------------------------------------------- 512 -> 256 fold
 // h = (t[0..7] + 38 * t[8..15]) mod 2^256-38, weakly reduced
+#ifndef AFC_FOLD_SHIFT
+#define AFC_FOLD_SHIFT 0        // 1: 38 * hi as (hi << 5) + (hi << 2) + (hi << 1) on the ALU pipe instead of 8 IMAD.WIDE (experiment)
+#endif
 AFC_HD void fe_fold16(fe& h, const uint32_t* t) {
-#if AFC_DEVICE_CODE && AFC_FE_PTX
+#if AFC_DEVICE_CODE && AFC_FE_PTX && AFC_FOLD_SHIFT
+    // 38 * hi = (hi << 5) + (hi << 2) + (hi << 1): nine limbs each (funnel shifts, no carries), two add chains, then + lo.
+    uint32_t a[9], b[9], c[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint32_t lo_ = i ? t[8 + i - 1] : 0u, hi_ = i < 8 ? t[8 + i] : 0u;
+        a[i] = __funnelshift_l(lo_, hi_, 5); b[i] = __funnelshift_l(lo_, hi_, 2); c[i] = __funnelshift_l(lo_, hi_, 1);
+    }
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\taddc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\taddc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\taddc.cc.u32 %6, %6, %15;\n\taddc.cc.u32 %7, %7, %16;\n\taddc.u32 %8, %8, %17;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\taddc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\taddc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\taddc.cc.u32 %6, %6, %15;\n\taddc.cc.u32 %7, %7, %16;\n\taddc.u32 %8, %8, %17;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+        : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]));
+    uint32_t r0 = t[0], r1 = t[1], r2 = t[2], r3 = t[3], r4 = t[4], r5 = t[5], r6 = t[6], r7 = t[7], top = a[8];
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\taddc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\taddc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\taddc.cc.u32 %6, %6, %15;\n\taddc.cc.u32 %7, %7, %16;\n\taddc.u32 %8, %8, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(top)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+    uint32_t k = top * 38u, c2;          // top <= 38
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.cc.u32 %7, %7, 0;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(c2)
+        : "r"(k));
+    r0 += c2 * 38u;
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#elif AFC_DEVICE_CODE && AFC_FE_PTX
     uint32_t r0 = t[0], r1 = t[1], r2 = t[2], r3 = t[3], r4 = t[4], r5 = t[5], r6 = t[6], r7 = t[7], ce;
     const uint32_t k38 = 38u;
     // even columns of 38*hi accumulate in place (aligned pairs), one chain

@@ -100,6 +100,10 @@ constexpr int KC_GMAX = AFC_KC_GMAX;
 #ifndef AFC_CACHED_MINB
 #define AFC_CACHED_MINB 3      // 5 (96 registers, 20 warps/SM) was measured: 4.5 ms, spills
 #endif
+#ifndef AFC_CACHED_THREADS
+#define AFC_CACHED_THREADS 128
+#endif
+constexpr int KC_THREADS = AFC_CACHED_THREADS;
 
 // Shared body: thread t of T handles positions t, t + T, t + 2T, ... of an ORDER of the credentials (G of them; lanes stay
 // adjacent in that order).  item(p) -> credential index of position p: the identity for the key-set kernel without a
@@ -557,7 +561,7 @@ k_kc_scatter(KeyCacheDev kc, uint32_t n) {
 }
 // (Fusing k_ed_hram into this kernel was measured and dropped: 8.87 ms vs 6.65 + 1.29 ms per 1 M — the SHA-512 state pushes
 // the register allocation of the curve loop around and nothing overlaps that did not already.)
-__global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
+__global__ void __launch_bounds__(KC_THREADS, AFC_CACHED_MINB)
 k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
                    int G, uint8_t* __restrict__ ok) {
     const uint32_t n_hot = kc.state[KS_NHOT];
@@ -839,8 +843,9 @@ static int pick_group_for(uint32_t n, const void* kernel, int slot, uint64_t c_m
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ED_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 3; }
-        resident[slot] = sms * per_sm * ED_THREADS;
+        const int threads = slot == 0 ? KC_THREADS : ED_THREADS;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 3; }
+        resident[slot] = sms * per_sm * threads;
     }
     const uint64_t R = (uint64_t)resident[slot];
     int best = 1; uint64_t best_cost = ~0ull;
@@ -960,7 +965,7 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
     if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
     const int G = pick_group(n, (const void*)k_ed_verify_cached);
     const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, ED_THREADS), ED_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+    AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
     launch_generic_verify(cb, pks, sigs, scratch_k, n, ok, kc.cold, kc.state + KS_NCOLD, s, lg);
     return cudaGetLastError();
 }

@@ -2,7 +2,7 @@
 # build_variant.sh NAME "-DFLAG=... ..."  ->  agentfield_b200/variants/libafcrypto_NAME.so  (experiment builds; load with AFC_LIB=...)
 set -e
 name=$1; flags=$2
-root=$(cd "$(dirname "$0")/../.." && pwd)
+root=$(cd "$(dirname "$0")/.." && pwd)
 obj=$root/build/variants/$name; mkdir -p $obj $root/agentfield_b200/variants
 cd $root/agentfield_b200/csrc
 for f in k_hash k_ed25519 afcrypto afc_ingest; do

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One cold 1 M-credential verify (BASELINE configs[1]) between cudaProfilerStart/Stop, for ncu --set full."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import agentfield_b200 as afb
 import bench
