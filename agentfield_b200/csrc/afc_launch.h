@@ -125,9 +125,11 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
 size_t ed_key_table_bytes(uint32_t n_keys);
 size_t ed_key_bases_bytes(uint32_t n_keys);     // scratch for ed_build_key_tables
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg);
+size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n);
+// scratch_perm: ed_keyed_scratch_bytes() bytes for the issuer-bucketed order (nullptr = credential order)
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
-                                  uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg);
+                                  uint8_t* ok, uint32_t* scratch_k, uint32_t* scratch_perm, cudaStream_t s, LaunchLog* lg);
 // ct16: the 48 KB constant-time table (ed_build_ct_table) or nullptr for the fast, variable-time fixed-base multiplication
 size_t ed_ct_table_bytes();
 cudaError_t ed_build_ct_table(const void* comb, void* ct16, cudaStream_t s, LaunchLog* lg);

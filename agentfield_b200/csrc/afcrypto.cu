@@ -357,7 +357,8 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         CK(sl.out.reserve((size_t)cnt * A.out_item + 16));
         if (A.a) CK(sl.a.reserve((size_t)cnt * A.a_item + 16));
         if (A.b) CK(sl.b.reserve((size_t)cnt * A.b_item + 16));
-        if (A.op == OP_VERIFY || A.op == OP_VERIFY_KEYED) CK(sl.k.reserve((size_t)cnt * 32));
+        if (A.op == OP_VERIFY) CK(sl.k.reserve((size_t)cnt * 32));
+        if (A.op == OP_VERIFY_KEYED) CK(sl.k.reserve((size_t)cnt * 32 + launch::ed_keyed_scratch_bytes(A.keyset->n_keys, cnt)));
         uint32_t kbase = 0; size_t kbytes = 0;
         if (A.op == OP_HMAC) {
             kbase = A.koff[i0]; kbytes = A.koff[i1] - kbase;
@@ -400,7 +401,8 @@ int run_host_batch(afc_ctx* ctx, const BatchArgs& A) {
         case OP_VERIFY_KEYED: {
             CK(h2d(sl, sl.koff.p, A.key_index + i0, (size_t)cnt * 4, pin_ki, &used));
             e = launch::ed_verify_keyed_batch(ctx->comb, A.keyset->d_tabs, A.keyset->d_valid, A.keyset->d_pks, A.keyset->n_keys,
-                                              (const uint32_t*)sl.koff.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p, sl.stream, lc);
+                                              (const uint32_t*)sl.koff.p, sl.b.p, d_base, d_off, cnt, sl.out.p, (uint32_t*)sl.k.p,
+                                              (uint32_t*)(sl.k.p + (size_t)cnt * 32), sl.stream, lc);
             break;
         }
         case OP_SIGN: e = launch::ed_sign_batch(ctx->comb, afc_internal_sign_table(ctx), sl.a.p, d_base, d_off, cnt, sl.out.p, sl.stream, lc); break;
@@ -935,9 +937,9 @@ int afc_ed25519_verify_keyed_batch_dev(afc_ctx* ctx, afc_keyset* ks, const uint3
     CallLog lc(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* d_k = nullptr;
-    if (n) CK(cudaMallocAsync((void**)&d_k, (size_t)n * 32, st));
+    if (n) CK(cudaMallocAsync((void**)&d_k, (size_t)n * 32 + launch::ed_keyed_scratch_bytes(ks->n_keys, n), st));
     cudaError_t e = launch::ed_verify_keyed_batch(ctx->comb, ks->d_tabs, ks->d_valid, ks->d_pks, ks->n_keys, d_key_index, d_sigs, d_msgs,
-                                                  d_msg_off, n, d_ok, d_k, st, lc);
+                                                  d_msg_off, n, d_ok, d_k, n ? d_k + (size_t)n * 8 : nullptr, st, lc);
     if (n) cudaFreeAsync(d_k, st);
     CK(e);
     return AFC_OK;

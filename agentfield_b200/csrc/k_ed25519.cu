@@ -30,6 +30,26 @@ __device__ __forceinline__ void store_words8(uint8_t* p, const uint32_t* w) {
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// One atomicAdd per distinct target among the lanes of a warp that call this together: the leader of each group of lanes
+// with the same address adds the group's size and every lane gets its own slot (credentials of one issuer often arrive
+// together, and the cold list has a single counter).
+__device__ __forceinline__ uint32_t kc_grouped_add(uint32_t* addr) {
+    const uint32_t mask = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)addr);
+    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(addr, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1));
+}
+
+// Plain fills as kernels of our own: cudaMemsetAsync in these streams was measured to cost anything from microseconds to
+// ~0.7 ms per call depending on what else the driver had in flight (a 16-byte memset per staged chunk: +3.5 ms per host call).
+__global__ void __launch_bounds__(256)
+k_fill_u32(uint32_t* __restrict__ p, uint32_t v, uint64_t n) {
+    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) { *(uint4*)(p + i) = make_uint4(v, v, v, v); return; }
+    for (; i < n; i++) p[i] = v;
+}
 // one thread per BASE_CHUNK consecutive entries of one row of the base-point table (afc_init, once per context)
 __global__ void __launch_bounds__(32)
 k_ed_build_tables(ge_precomp* base) {
@@ -318,11 +338,54 @@ k_ed_hram_keyed(const uint8_t* __restrict__ key_pks, const uint32_t* __restrict_
     store_words8((uint8_t*)(k_out + 8ull * i), k);
 }
 
+// bucketing of an explicit key set's batch by key index (counting sort: histogram, scan, scatter), so that the table-driven kernel
+// walks it issuer by issuer like the transparent cache does; indices past the key set share one extra bucket (their ok is 0 anyway)
+__global__ void __launch_bounds__(256)
+k_ks_hist(const uint32_t* __restrict__ key_index, uint32_t n_keys, uint32_t n, uint32_t* __restrict__ bucket) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key_index[i];
+    kc_grouped_add(&bucket[k < n_keys ? k : n_keys]);
+}
+__global__ void __launch_bounds__(1024)
+k_ks_scan(uint32_t* __restrict__ bucket, uint32_t m) {          // exclusive scan of m counters in place, ONE CTA
+    __shared__ uint32_t s_part[32], s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t id = base + threadIdx.x, v = id < m ? bucket[id] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t p = s_part[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, p, d); if (threadIdx.x >= d) p += y; }
+            s_part[threadIdx.x] = p;
+        }
+        __syncthreads();
+        const uint32_t warp_off = (threadIdx.x >> 5) ? s_part[(threadIdx.x >> 5) - 1] : 0;
+        if (id < m) bucket[id] = s_carry + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_part[31];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+k_ks_scatter(const uint32_t* __restrict__ key_index, uint32_t n_keys, uint32_t n, uint32_t* __restrict__ bucket, uint32_t* __restrict__ perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key_index[i];
+    perm[kc_grouped_add(&bucket[k < n_keys ? k : n_keys])] = i;
+}
+
 __global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                   const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
-                  const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok) {
-    table_verify_group([](uint32_t p) { return p; }, [&](uint32_t i, const ge_precomp*& atab) {
+                  const uint32_t* __restrict__ ks, uint32_t n, uint32_t T, int G, uint8_t* __restrict__ ok, const uint32_t* __restrict__ perm) {
+    table_verify_group([&](uint32_t p) { return perm ? perm[p] : p; }, [&](uint32_t i, const ge_precomp*& atab) {
         uint32_t key = key_index[i];
         if (key >= n_keys || !valid[key]) return false;      // unknown index or undecodable key: ok = 0
         atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
@@ -363,26 +426,6 @@ __device__ __forceinline__ bool kc_equal(const uint32_t* a, const uint8_t* p) {
 #pragma unroll
     for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
     return d == 0;
-}
-// One atomicAdd per distinct target among the lanes of a warp that call this together: the leader of each group of lanes
-// with the same address adds the group's size and every lane gets its own slot (credentials of one issuer often arrive
-// together, and the cold list has a single counter).
-__device__ __forceinline__ uint32_t kc_grouped_add(uint32_t* addr) {
-    const uint32_t mask = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)addr);
-    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(addr, (uint32_t)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    return base + (uint32_t)__popc(mask & ((1u << lane) - 1));
-}
-
-// Plain fills as kernels of our own: cudaMemsetAsync in these streams was measured to cost anything from microseconds to
-// ~0.7 ms per call depending on what else the driver had in flight (a 16-byte memset per staged chunk: +3.5 ms per host call).
-__global__ void __launch_bounds__(256)
-k_fill_u32(uint32_t* __restrict__ p, uint32_t v, uint64_t n) {
-    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) { *(uint4*)(p + i) = make_uint4(v, v, v, v); return; }
-    for (; i < n; i++) p[i] = v;
 }
 // start of a call: per-call counters, next epoch, per-id credential counts zeroed
 __global__ void __launch_bounds__(256)
@@ -977,14 +1020,27 @@ cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs,
     launch_key_build(b, n_keys, s, s, nullptr, lg);
     return cudaGetLastError();
 }
+static inline size_t keyed_bucket_words(uint32_t n_keys) { return ((size_t)n_keys + 1 + 3) & ~(size_t)3; }     // keeps what follows 16-byte aligned
+size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n) { return (keyed_bucket_words(n_keys) + (size_t)n) * 4; }
+// scratch_perm: ed_keyed_scratch_bytes(n_keys, n) bytes, 16-byte aligned (bucket[n_keys + 1] then perm[n]), or nullptr = credential order
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
-                                  uint8_t* ok, uint32_t* scratch_k, cudaStream_t s, LaunchLog* lg) {
+                                  uint8_t* ok, uint32_t* scratch_k, uint32_t* scratch_perm, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
+    const uint32_t* perm = nullptr;
+    if (scratch_perm && n >= 4096) {                     // small batches: one wave anyway, the three extra launches would cost more
+        uint32_t* bucket = scratch_perm;
+        uint32_t* perm_w = scratch_perm + keyed_bucket_words(n_keys);
+        AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for(((uint64_t)n_keys + 4) / 4, 256), 256, 0, s>>>(bucket, 0u, (uint64_t)n_keys + 1));
+        AFC_LAUNCH(lg, "k_ks_hist", s, k_ks_hist<<<blocks_for(n, 256), 256, 0, s>>>(key_index, n_keys, n, bucket));
+        AFC_LAUNCH(lg, "k_ks_scan", s, k_ks_scan<<<1, 1024, 0, s>>>(bucket, n_keys + 1));
+        AFC_LAUNCH(lg, "k_ks_scatter", s, k_ks_scatter<<<blocks_for(n, 256), 256, 0, s>>>(key_index, n_keys, n, bucket, perm_w));
+        perm = perm_w;
+    }
     AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
     const int G = pick_group(n, (const void*)k_ed_verify_keyed);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, T, G, ok));
+    AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, T, G, ok, perm));
     return cudaGetLastError();
 }
 // ct16 != nullptr selects the constant-time kernels (48 KB of dynamic shared memory for the table)

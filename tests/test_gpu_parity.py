@@ -321,7 +321,7 @@ def test_keyed_verify_equals_generic_verify_and_go_rules(ctx):
     ks.close()
     # random keys, ragged messages, corruption in every field; out-of-range key index -> 0
     rng = np.random.default_rng(0xAF12)
-    nk, n = 64, 4000
+    nk, n = 64, 12000                                     # >= 4096: the batch is bucketed by key index before the table-driven kernel
     seeds = rng.integers(0, 256, (nk, 32), dtype=np.uint8)
     kpks = ctx.pubkeys(seeds)
     ki = rng.integers(0, nk, n).astype(np.uint32)
