@@ -143,6 +143,8 @@ def verify_bundle(bundle, ctx=None, trusted_checkpoints=None, verified_at=""):
             step(2, "Parsing VC structure", False, error="Invalid VC format: %s" % ex)
             res["error"] = "Invalid VC format: not a recognized AgentField VC structure"
             return res
+    elif isinstance(bundle, dict):
+        bundle = json.loads(json.dumps(bundle), parse_int=float)      # work on a copy: documents are normalised in place below
     if not isinstance(bundle, dict) or not bundle.get("workflow_id"):
         step(2, "Parsing VC structure", False, error="Invalid VC format: not a recognized AgentField VC structure")
         res["error"] = "Invalid VC format: not a recognized AgentField VC structure"
