@@ -189,6 +189,71 @@ AFC_HD void fe_sub(fe& h, const fe& f, const fe& g) {
 AFC_HD void fe_neg(fe& h, const fe& f) { fe z; fe_0(z); fe_sub(h, z, f); }
 AFC_HD void fe_dbl(fe& h, const fe& f) { fe_add(h, f, f); }
 
+// h = f + (g & keep)  when sgn == 0,  h = f - (g & keep)  when sgn == 0xffffffff  (keep: 0 or 0xffffffff), weakly reduced.
+// ONE instruction stream for both signs: the four lanes that share a point in the quad kernels (k_ed25519.cu) each need a
+// different one of B-A, B+A, D-C, D+C at the same moment.  f - g is computed as f + ~g + 1: a missing carry-out is a borrow, and
+// the correction (2^256 = 38) changes sign with the operation.
+AFC_HD void fe_addsub_m_c(fe& h, const fe& f, const fe& g, uint32_t keep, uint32_t sgn) {
+    const uint32_t cin = sgn & 1u;
+    uint64_t c = cin;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)f.v[i] + ((g.v[i] & keep) ^ sgn); r[i] = (uint32_t)c; c >>= 32; }
+    const uint32_t w = (uint32_t)c ^ cin;                   // add: carried out; subtract: borrowed
+    const uint32_t k = (0u - w) & 38u;
+    c = cin;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)r[i] + (i ? sgn : (k ^ sgn)); r[i] = (uint32_t)c; c >>= 32; }
+    const uint32_t w2 = (uint32_t)c ^ cin;
+    r[0] += (0u - w2) & ((38u ^ sgn) + cin);                // +38 or -38; cannot carry or borrow again
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+}
+AFC_HD void fe_addsub_m(fe& h, const fe& f, const fe& g, uint32_t keep, uint32_t sgn) {
+#if AFC_DEVICE_CODE && AFC_FE_PTX
+    const uint32_t cin = sgn & 1u;
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7;             // (g & keep) ^ sgn as ONE LOP3 each (left to ptxas `keep` becomes a predicate and a SEL)
+#define AFC_KEEP_XOR(t, w) asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(t) : "r"(g.v[w]), "r"(keep), "r"(sgn))
+    AFC_KEEP_XOR(t0, 0); AFC_KEEP_XOR(t1, 1); AFC_KEEP_XOR(t2, 2); AFC_KEEP_XOR(t3, 3);
+    AFC_KEEP_XOR(t4, 4); AFC_KEEP_XOR(t5, 5); AFC_KEEP_XOR(t6, 6); AFC_KEEP_XOR(t7, 7);
+#undef AFC_KEEP_XOR
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, c, dump;
+    asm("add.cc.u32 %9, %26, 0xffffffff;\n\t"           // CC.CF = cin
+        "addc.cc.u32 %0, %10, %18;\n\t"
+        "addc.cc.u32 %1, %11, %19;\n\t"
+        "addc.cc.u32 %2, %12, %20;\n\t"
+        "addc.cc.u32 %3, %13, %21;\n\t"
+        "addc.cc.u32 %4, %14, %22;\n\t"
+        "addc.cc.u32 %5, %15, %23;\n\t"
+        "addc.cc.u32 %6, %16, %24;\n\t"
+        "addc.cc.u32 %7, %17, %25;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(c), "=r"(dump)
+        : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+          "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"(t4), "r"(t5), "r"(t6), "r"(t7), "r"(cin));
+    const uint32_t w = c ^ cin;
+    const uint32_t kk = ((0u - w) & 38u) ^ sgn;
+    uint32_t c2;
+    asm("add.cc.u32 %9, %12, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %11;\n\t"
+        "addc.cc.u32 %5, %5, %11;\n\t"
+        "addc.cc.u32 %6, %6, %11;\n\t"
+        "addc.cc.u32 %7, %7, %11;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(c2), "=r"(dump)
+        : "r"(kk), "r"(sgn), "r"(cin));
+    const uint32_t w2 = c2 ^ cin;
+    r0 += (0u - w2) & ((38u ^ sgn) + cin);
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    fe_addsub_m_c(h, f, g, keep, sgn);
+#endif
+}
+
 // ---------------------------------------------------------------------------------- 512 -> 256 fold
 // h = (t[0..7] + 38 * t[8..15]) mod 2^256-38, weakly reduced
 #ifndef AFC_FOLD_SHIFT

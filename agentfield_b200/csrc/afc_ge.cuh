@@ -100,6 +100,34 @@ AFC_HD void ge_maddsub(ge_p1p1& r, const ge_p3& p, const ge_precomp& q, int neg)
     fe_add(dpc, d, c); fe_sub(dmc, d, c);
     fe_select(r.Z, dpc, dmc, neg); fe_select(r.T, dmc, dpc, neg);
 }
+// ---- the same mixed addition on FOUR lanes (k_ed_verify_quad) -------------------------------------------------------------
+// Lane `role` of a quad owns one coordinate of the running point (0 X, 1 Y, 2 Z, 3 T) and does 2 of the 7 (+1 idle)
+// multiplications; everything else it needs arrives by shuffle from lane q0 + src.  One step is
+//   stage 1   u = own ± (shfl(own, src1) & keep1)        X - Y | Y + X | Z + Z | T + 0
+//   round 1   m = u * v, v = the lane's 32 bytes of the table entry (or 1)         -A' | B' | D | C      (A', B', C, D of ge_maddsub)
+//   stage 2   w = shfl(m, srcA2) ± shfl(m, srcB2)        F = D∓C | H = B'+A' | G = D±C | E = B'-A'      (signs follow `neg`)
+//   round 2   own = w * shfl(w, src3)                    X3 = F E | Y3 = H G | Z3 = G F | T3 = E H
+// so the layout is the same after every step.  Signs are masks for fe_addsub_m (0: add, ~0: subtract).  The plan is plain data
+// so that tests/hostsim can replay the four lanes on the CPU against ge_maddsub + ge_p1p1_to_p3.
+struct quad_plan { int src1, srcA2, srcB2, src3; uint32_t keep1, sgn1, sgn2, v_off; int v_load; };
+AFC_HD quad_plan ge_quad_plan(int role, int neg) {
+    quad_plan p;
+    const uint32_t nm = 0u - (uint32_t)(neg != 0);
+    p.src1 = role == 0 ? 1 : role == 1 ? 0 : role;
+    p.keep1 = role == 3 ? 0u : 0xffffffffu;
+    p.sgn1 = role == 0 ? 0xffffffffu : 0u;
+    p.srcA2 = (role & 1) ? 1 : 2;
+    p.srcB2 = (role & 1) ? 0 : 3;
+    p.sgn2 = role == 0 ? ~nm : role == 1 ? 0xffffffffu : role == 2 ? nm : 0u;
+    p.src3 = role == 0 ? 3 : role == 1 ? 2 : role == 2 ? 0 : 1;
+    // bytes into the 96-byte entry {ypx, ymx, xy2d}: the X lane multiplies by ymx (ypx when subtracting), the Y lane the other way round
+    p.v_off = role == 3 ? 64u : (((uint32_t)(role == 0) ^ (uint32_t)(neg != 0)) ? 32u : 0u);
+    p.v_load = role != 2;
+    return p;
+}
+// what a lane multiplies by when it has nothing to load: 1 (Z lane; digit 0 on the X and Y lanes) or 0 (digit 0 on the T lane)
+AFC_HD void ge_quad_neutral(fe& v, int role) { fe_0(v); v.v[0] = role == 3 ? 0u : 1u; }
+
 template <class F = FeInline>
 AFC_HD void ge_p3_to_precomp(ge_precomp& r, const ge_p3& p) {
     fe zi, x, y, xy, d2;

@@ -87,6 +87,7 @@ enum KcState {
     KS_REBUILD = 8,    // the persistent hash table must be rebuilt (something was evicted)
     KS_EVICTED = 9,    // tables evicted in the current call
     KS_TOTAL_BUILT = 10, KS_TOTAL_EVICTED = 11, KS_CALLS = 12,
+    KS_QTILE = 13,     // next position of the order the four-lane kernel hands to a warp
     KS_WORDS = 16
 };
 struct KeyCache {
@@ -113,6 +114,7 @@ struct KeyCache {
     uint32_t* cand;         // representatives that want a table (at most n / KC_AMORTISE)
     uint32_t* perm;         // hot credentials bucketed by cache id (KS_NHOT entries)
     uint32_t* cold;         // cold credentials (KS_NCOLD entries)
+    void* pts;              // 96 bytes per hot position: the projective result of the four-lane kernel, until k_ed_quad_finish
     // the cache work of a call runs on `side` (a high-priority stream) and `side2` between ev_fork and ev_join, while the
     // caller's stream computes H(R||A||M), which does not depend on the cache
     cudaStream_t side, side2;
@@ -126,7 +128,7 @@ size_t ed_key_table_bytes(uint32_t n_keys);
 size_t ed_key_bases_bytes(uint32_t n_keys);     // scratch for ed_build_key_tables
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg);
 size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n);
-// scratch_perm: ed_keyed_scratch_bytes() bytes for the issuer-bucketed order (nullptr = credential order)
+// scratch_perm: ed_keyed_scratch_bytes() bytes, 32-byte aligned: projective results, then the issuer-bucketed order (nullptr = credential order, one-thread kernel)
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                                   uint8_t* ok, uint32_t* scratch_k, uint32_t* scratch_perm, cudaStream_t s, LaunchLog* lg);

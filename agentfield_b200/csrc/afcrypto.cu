@@ -170,9 +170,9 @@ struct CallLog {
 
 // ---- issuer-key cache management ------------------------------------------------------------------------------
 void kc_free_call_buffers(launch::KeyCache& k) {
-    void* ps[] = {k.bslots, k.rep, k.kid, k.cnt, k.dlist, k.cand, k.perm, k.cold};
+    void* ps[] = {k.bslots, k.rep, k.kid, k.cnt, k.dlist, k.cand, k.perm, k.cold, k.pts};
     for (void* p : ps) if (p) cudaFree(p);
-    k.bslots = k.rep = k.kid = k.cnt = k.dlist = k.cand = k.perm = k.cold = nullptr;
+    k.bslots = k.rep = k.kid = k.cnt = k.dlist = k.cand = k.perm = k.cold = nullptr; k.pts = nullptr;
 }
 void kc_free(afc_ctx* ctx) {
     launch::KeyCache& k = ctx->kc;
@@ -221,7 +221,8 @@ const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
         uint64_t cap = 1; while (cap < 2 * want) cap <<= 1;
         if (cap > 0x80000000ull) { ctx->kc_call_cap = 0; return nullptr; }                    // beyond the 32-bit tables: generic kernel
         bool ok = dmalloc(&k.bslots, (size_t)cap * 4) && dmalloc(&k.rep, want * 4) && dmalloc(&k.kid, want * 4) && dmalloc(&k.cnt, want * 4) &&
-                  dmalloc(&k.dlist, want * 4) && dmalloc(&k.cand, want * 4) && dmalloc(&k.perm, want * 4) && dmalloc(&k.cold, want * 4);
+                  dmalloc(&k.dlist, want * 4) && dmalloc(&k.cand, want * 4) && dmalloc(&k.perm, want * 4) && dmalloc(&k.cold, want * 4) &&
+                  dmalloc(&k.pts, want * 96);
         if (!ok) { cudaGetLastError(); kc_free_call_buffers(k); ctx->kc_call_cap = 0; return nullptr; }
         k.bmask = (uint32_t)(cap - 1); ctx->kc_call_cap = (uint32_t)(want > 0xffffffffull ? 0xffffffffu : want);
     }

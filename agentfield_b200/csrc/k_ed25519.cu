@@ -67,9 +67,13 @@ k_ed_build_ct16(const ge_precomp* __restrict__ base, ge_precomp* __restrict__ ct
 
 __global__ void __launch_bounds__(ED_THREADS)
 k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
-          const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out) {
+          const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out, const uint32_t* __restrict__ list = nullptr,
+          const uint32_t* __restrict__ n_list = nullptr) {
+    // with a list: only the credentials the issuer-key cache left to the generic kernel (the four-lane kernel hashes its own)
+    if (list) { n = *n_list; if (blockIdx.x * blockDim.x >= n) return; }
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (list) i = list[i];
     uint32_t pk[8], sig[16], k[8];
     load_words8(pk, pks + 32ull * i);
     load_words8(sig, sigs + 64ull * i);          // only R is hashed
@@ -434,7 +438,7 @@ k_kc_begin(KeyCacheDev kc) {
     for (uint32_t i = t; i <= kc.max_keys; i += gridDim.x * blockDim.x) kc.bucket[i] = 0;
     if (t == 0) {
         kc.state[KS_NHOT] = 0; kc.state[KS_NCOLD] = 0; kc.state[KS_DISTINCT] = 0; kc.state[KS_NBUILD] = 0; kc.state[KS_NCAND] = 0;
-        kc.state[KS_REBUILD] = 0; kc.state[KS_EVICTED] = 0;
+        kc.state[KS_REBUILD] = 0; kc.state[KS_EVICTED] = 0; kc.state[KS_QTILE] = 0;
         kc.state[KS_EPOCH] += 1; kc.state[KS_CALLS] += 1;
     }
 }
@@ -616,6 +620,225 @@ k_ed_verify_cached(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const ui
         atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
         return true;
     }, comb, sigs, ks, n_hot, T, G, ok);
+}
+
+// ---- table-driven verification on FOUR lanes per credential (experiment, AFC_VERIFY_QUAD=1|2) --------------------------------
+// k_ed_verify_cached / _keyed above keep a whole point, a table entry and the multiplier's accumulators in one thread: 124
+// registers, 4 warps per scheduler, the 64-bit multiplier 77 % busy and no room on the SM for the hashing to run beside it
+// (DESIGN.md §4).  Here a QUAD of lanes shares one credential (ge_quad_plan, afc_ge.cuh): each lane owns one coordinate and does 2
+// of the 8 multiplication slots of a mixed addition (7 used), operands arrive by shuffle, and the lane loads only its own 32 bytes
+// of the 96-byte table entry.  A lane needs 80 registers, so six warps per scheduler are resident, and (mode 2) the SAME warps do
+// the hashing: a warp takes 32 consecutive positions of the issuer-bucketed order, every lane first hashes ONE credential
+// (H(R || A || M) mod L, ALU pipe) and leaves its recoded scalars in shared memory, then every quad walks four credentials
+// through the tables (multiplier pipe).  The projective result goes to `pts` (3 field elements per position); k_ed_quad_finish
+// shares one field inversion per CTA of 2048 credentials, encodes and compares with R.
+// What the measurements say (profiles/r02_quad_*): the multiplier is busier (82 %) but has more to do — 8 slots for 7 products and
+// the moves ptxas puts on the same pipe — so the kernel takes 4.28 + 0.23 ms against 3.90; fused, hashing in bucketed order reads
+// its messages at random (3.6 GB of DRAM traffic for 0.6 GB of input) and the two code bodies miss the instruction cache (14 % of
+// stalls): 5.60 ms, no better than hashing first.  Not the default.
+#ifndef AFC_QUAD_THREADS
+#define AFC_QUAD_THREADS 128
+#endif
+#ifndef AFC_QUAD_MINB
+#define AFC_QUAD_MINB 6
+#endif
+constexpr int QD_THREADS = AFC_QUAD_THREADS;
+constexpr int QF_THREADS = 256, QF_G = 8;
+static_assert(BASE_W == 16, "the quad kernel walks one base-table row per two key-table rows");
+
+struct QuadSlot {                 // what the owner lane of a credential leaves for the quad that walks it
+    uint32_t kt[8], st[8];        // signed radix-256 digits of k, signed radix-65536 digits of S
+    const ge_precomp* atab;       // the issuer's table
+};
+// where the credentials, their order and their keys come from
+struct QuadCached {               // transparent cache: hot credentials in bucketed order
+    KeyCacheDev kc; const uint8_t* pks;
+    __device__ __forceinline__ uint32_t count() const { return kc.state[KS_NHOT]; }
+    __device__ __forceinline__ uint32_t item(uint32_t p) const { return kc.perm[p]; }
+    __device__ __forceinline__ bool key(uint32_t i, const ge_precomp*& atab, const uint8_t*& pk) const {
+        const uint32_t id = kc.kid[kc.rep[i]];
+        pk = pks + 32ull * i;
+        if (!kc.valid[id]) return false;
+        atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
+        return true;
+    }
+};
+struct QuadKeyed {                // explicit key set
+    const ge_precomp* tabs; const uint8_t* valid; const uint8_t* key_pks; const uint32_t* key_index; uint32_t n_keys;
+    const uint32_t* perm; uint32_t n;
+    __device__ __forceinline__ uint32_t count() const { return n; }
+    __device__ __forceinline__ uint32_t item(uint32_t p) const { return perm ? perm[p] : p; }
+    __device__ __forceinline__ bool key(uint32_t i, const ge_precomp*& atab, const uint8_t*& pk) const {
+        const uint32_t k = key_index[i];
+        if (k >= n_keys) return false;
+        pk = key_pks + 32ull * k;
+        if (!valid[k]) return false;
+        atab = tabs + (size_t)k * COMB_ROWS * COMB_COLS;
+        return true;
+    }
+};
+
+// The neutral table entry {y + x, y - x, 2dxy} = {1, 1, 0}: what a digit 0 adds, and (its first element) what the Z lane multiplies by.
+// Loading it like any other entry keeps the loads unconditional and the instruction stream free of selects.
+__device__ const uint32_t g_quad_neutral[24] = {1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+// ge_quad_plan(role, neg) as per-lane constants (absolute source lanes; the two things that depend on the digit's sign as base ^ flip)
+struct QuadLane {
+    int s1, sA2, sB2, s3;
+    uint32_t keep1, sgn1, s2base, s2flip, voff_base, voff_flip;
+    bool zlane;
+};
+__device__ __forceinline__ QuadLane quad_lane(int role, int q0) {
+    const quad_plan a = ge_quad_plan(role, 0), b = ge_quad_plan(role, 1);
+    QuadLane L;
+    L.s1 = q0 + a.src1; L.sA2 = q0 + a.srcA2; L.sB2 = q0 + a.srcB2; L.s3 = q0 + a.src3;
+    L.keep1 = a.keep1; L.sgn1 = a.sgn1;
+    L.s2base = a.sgn2; L.s2flip = a.sgn2 ^ b.sgn2;
+    L.voff_base = a.v_off; L.voff_flip = a.v_off ^ b.v_off;
+    L.zlane = !a.v_load;
+    if (L.zlane) { L.voff_base = 0; L.voff_flip = 0; }
+    return L;
+}
+// the lane's 32 bytes of row[|d| - 1], or of the neutral entry (d == 0, Z lane)
+__device__ __forceinline__ void quad_load(fe& v, const ge_precomp* row, int d, const QuadLane& L) {
+    const uint32_t nm = (uint32_t)(d >> 31);
+    const int m = d < 0 ? -d : d;
+    const char* e = (m == 0 || L.zlane) ? (const char*)g_quad_neutral : (const char*)(row + (m - 1));
+    const uint32_t* p = (const uint32_t*)(e + (L.voff_base ^ (L.voff_flip & nm)));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.v[0]), "=r"(v.v[1]), "=r"(v.v[2]), "=r"(v.v[3]), "=r"(v.v[4]), "=r"(v.v[5]), "=r"(v.v[6]), "=r"(v.v[7]) : "l"(p));
+}
+__device__ __forceinline__ void quad_madd(fe& C, const fe& v, int d, const QuadLane& L) {
+    const uint32_t nm = (uint32_t)(d >> 31);
+    fe p, u, m, a, b, w, x;
+    fe_shfl(p, C, L.s1);
+    fe_addsub_m(u, C, p, L.keep1, L.sgn1);
+    fe_mul(m, u, v);
+    fe_shfl(a, m, L.sA2); fe_shfl(b, m, L.sB2);
+    fe_addsub_m(w, a, b, 0xffffffffu, L.s2base ^ (L.s2flip & nm));
+    fe_shfl(x, w, L.s3);
+    fe_mul(C, w, x);
+}
+
+// Warps take tiles of the order from a counter: 32 positions at a time, except the first tile of a warp, which is 8, 16, 24 or 32
+// positions depending on where the warp sits — identical warps started together would otherwise hash together and multiply
+// together for the whole launch, and the two pipes would never be busy at the same time.
+template <class Src, bool FUSED>
+__global__ void __launch_bounds__(QD_THREADS, AFC_QUAD_MINB)
+k_ed_verify_quad(Src src, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
+                 const uint64_t* __restrict__ off, const uint32_t* __restrict__ ks, fe* __restrict__ pts, uint8_t* __restrict__ ok,
+                 uint32_t* __restrict__ tile_counter, uint32_t sms) {
+    __shared__ QuadSlot slots[QD_THREADS];
+    const uint32_t n = src.count();
+    const int lane = threadIdx.x & 31, role = lane & 3, quad = lane >> 2;
+    const QuadLane L = quad_lane(role, lane & ~3);
+    QuadSlot* wslots = slots + (threadIdx.x & ~31u);
+    uint32_t take = 8u * (1u + ((blockIdx.x / sms + (threadIdx.x >> 5)) & 3u));
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(tile_counter, take);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= n) break;
+        // ---- every lane prepares ONE credential: checks, k = H(R || A || M) mod L, recoded scalars
+        if ((uint32_t)lane < take) {
+            const uint32_t p = first + lane;
+            uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0}, S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const ge_precomp* atab = base;                                  // never read: all digits are 0 when the credential is bad
+            if (p < n) {
+                const uint32_t i = src.item(p);
+                const uint8_t* pkp = nullptr;
+                uint32_t sig[16];
+                load_words8(sig, sigs + 64ull * i);
+                load_words8(sig + 8, sigs + 64ull * i + 32);
+                const bool good = src.key(i, atab, pkp) && ed25519_sig_wellformed(sig);
+                if (good) {
+                    if (FUSED) {
+                        uint32_t pk[8];
+                        load_words8(pk, pkp);
+                        const uint64_t o0 = off[i], o1 = off[i + 1];
+                        ed25519_hram(k, pk, sig, msgs + o0, o1 - o0);
+                    } else load_words8(k, (const uint8_t*)(ks + 8ull * i));
+#pragma unroll
+                    for (int w = 0; w < 8; w++) S[w] = sig[8 + w];
+                } else atab = base;
+                ok[i] = (uint8_t)good;                                      // k_ed_quad_finish ands the comparison in
+            }
+            QuadSlot& mine = wslots[lane];
+            sc_recode256(mine.kt, k);
+            sc_recode_base(mine.st, S);
+#pragma unroll
+            for (int w = 0; w < 8; w++) { mine.kt[w] ^= 0x80808080u; mine.st[w] ^= 0x80008000u; }     // stored as signed digits
+            mine.atab = atab;
+        }
+        __syncwarp();
+        // ---- every quad walks up to four credentials: 32 additions from the issuer's table, 16 from the base-point table
+        const int nj = (int)(take >> 3);
+#pragma unroll 1
+        for (int j = 0; j < nj; j++) {
+            const uint32_t p = first + (uint32_t)(quad + 8 * j);
+            const QuadSlot& c = wslots[quad + 8 * j];
+            const int8_t* kb = (const int8_t*)c.kt;
+            const int16_t* sb = (const int16_t*)c.st;
+            const ge_precomp* atab = c.atab;
+            fe C; fe_0(C); C.v[0] = (role == 1 || role == 2) ? 1u : 0u;   // (0 : 1 : 1 : 0)
+            int d = kb[0];
+            fe v; quad_load(v, atab, d, L);
+#pragma unroll 1
+            for (int r = 0; r < BASE_ROWS; r++) {
+                const int d1 = kb[2 * r + 1];
+                fe v1; quad_load(v1, atab + (2 * r + 1) * COMB_COLS, d1, L);
+                quad_madd(C, v, d, L);
+                const int d2 = sb[r];
+                fe v2; quad_load(v2, base + (size_t)r * BASE_COLS, d2, L);
+                quad_madd(C, v1, d1, L);
+                if (r + 1 < BASE_ROWS) { d = kb[2 * r + 2]; quad_load(v, atab + (2 * r + 2) * COMB_COLS, d, L); }
+                quad_madd(C, v2, d2, L);
+            }
+            if (role < 3 && p < n) pts[3ull * p + role] = C;
+        }
+        __syncwarp();
+        take = 32;
+    }
+}
+
+// enc(X/Z, Y/Z) == R for every position, ONE field inversion per CTA (QF_THREADS x QF_G positions)
+template <class Src>
+__global__ void __launch_bounds__(QF_THREADS)
+k_ed_quad_finish(Src src, const fe* __restrict__ pts, const uint8_t* __restrict__ sigs, uint8_t* __restrict__ ok) {
+    __shared__ fe tree[2 * QF_THREADS];
+    const uint32_t n = src.count();
+    const uint32_t T = (n + QF_G - 1) / QF_G;
+    if (blockIdx.x * QF_THREADS >= T) return;                               // whole CTA past the end
+    const uint32_t t = blockIdx.x * QF_THREADS + threadIdx.x;
+    fe pz[QF_G], acc; fe_1(acc);
+#pragma unroll 1
+    for (int g = 0; g < QF_G; g++) {
+        const uint64_t p = (uint64_t)t + (uint64_t)g * T;
+        if (t < T && p < n) { fe z = pts[3 * p + 2]; FeCall::mul(acc, acc, z); }
+        pz[g] = acc;
+    }
+    fe inv;
+    fe_invert_cta<FeCall, QF_THREADS>(inv, acc, tree);
+    if (t >= T) return;
+#pragma unroll 1
+    for (int g = QF_G - 1; g >= 0; g--) {
+        const uint64_t p = (uint64_t)t + (uint64_t)g * T;
+        if (p >= n) continue;
+        fe zi, z = pts[3 * p + 2];
+        if (g > 0) FeCall::mul(zi, inv, pz[g - 1]); else fe_copy(zi, inv);
+        FeCall::mul(inv, inv, z);
+        fe x = pts[3 * p], y = pts[3 * p + 1];
+        FeCall::mul(x, x, zi); FeCall::mul(y, y, zi);
+        uint32_t enc[8], r[8];
+        fe_towords(enc, y);
+        enc[7] |= (uint32_t)fe_isnegative(x) << 31;
+        const uint32_t i = src.item((uint32_t)p);
+        load_words8(r, sigs + 64ull * i);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) diff |= enc[w] ^ r[w];
+        if (diff) ok[i] = 0;
+    }
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index.
@@ -924,6 +1147,25 @@ cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
     AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<blocks_for((uint64_t)BASE_ROWS * BASE_COLS / BASE_CHUNK, 32), 32, 0, s>>>((ge_precomp*)comb));
     return cudaGetLastError();
 }
+// AFC_VERIFY_QUAD: 0 = one thread per credential (k_ed_verify_cached / _keyed; default), 1 = four lanes per credential after
+// k_ed_hram, 2 = four lanes per credential with the hashing fused.  Measured on B200, 1 M credentials, tables cached: 5.07 / 5.66 /
+// 5.93 ms (the four-lane form keeps the multiplier 82 % busy instead of 77 %, but spends 8 multiplication slots on
+// the 7 products of a mixed addition and ~12 % more of the same pipe on register moves).  Kept as an experiment; same results.
+static int quad_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("AFC_VERIFY_QUAD"); m = e ? atoi(e) : 0; if (m < 0 || m > 2) m = 0; }
+    return m;
+}
+static uint32_t quad_sms() {
+    static thread_local int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+    return (uint32_t)sms;
+}
+// persistent grid of the four-lane kernel: every resident CTA slot, or fewer when the batch is small
+static uint32_t quad_grid(uint32_t n) {
+    const uint32_t full = quad_sms() * AFC_QUAD_MINB, need = blocks_for(((uint64_t)n + 7) / 8, QD_THREADS / 32);
+    return need < full ? need : full;
+}
 static void launch_generic_verify(const ge_precomp* cb, const uint8_t* pks, const uint8_t* sigs, const uint32_t* ks, uint32_t n, uint8_t* ok,
                                   const uint32_t* list, const uint32_t* n_list, cudaStream_t s, LaunchLog* lg) {
     static int variant = -1;
@@ -1004,11 +1246,21 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         if ((e = cudaStreamWaitEvent(q, kc.ev_rows, 0)) != cudaSuccess) return e;
     }
     if ((e = cudaEventRecord(kc.ev_join, q)) != cudaSuccess) return e;
-    AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
+    const int quad = kc.pts ? quad_mode() : 0;
+    if (quad != 2) AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k));
     if ((e = cudaStreamWaitEvent(s, kc.ev_join, 0)) != cudaSuccess) return e;
-    const int G = pick_group(n, (const void*)k_ed_verify_cached);
-    const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
-    AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+    if (quad) {
+        const QuadCached src{kc, pks};
+        if (quad == 2) {
+            AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadCached, true><<<quad_grid(n), QD_THREADS, 0, s>>>(src, cb, sigs, msgs, off, scratch_k, (fe*)kc.pts, ok, kc.state + KS_QTILE, quad_sms())));
+            AFC_LAUNCH(lg, "k_ed_hram", s, k_ed_hram<<<nb, ED_THREADS, 0, s>>>(pks, sigs, msgs, off, n, scratch_k, kc.cold, kc.state + KS_NCOLD));
+        } else AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadCached, false><<<quad_grid(n), QD_THREADS, 0, s>>>(src, cb, sigs, msgs, off, scratch_k, (fe*)kc.pts, ok, kc.state + KS_QTILE, quad_sms())));
+        AFC_LAUNCH(lg, "k_ed_quad_finish", s, k_ed_quad_finish<QuadCached><<<blocks_for(((uint64_t)n + QF_G - 1) / QF_G, QF_THREADS), QF_THREADS, 0, s>>>(src, (const fe*)kc.pts, sigs, ok));
+    } else {
+        const int G = pick_group(n, (const void*)k_ed_verify_cached);
+        const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
+        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+    }
     launch_generic_verify(cb, pks, sigs, scratch_k, n, ok, kc.cold, kc.state + KS_NCOLD, s, lg);
     return cudaGetLastError();
 }
@@ -1021,21 +1273,36 @@ cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs,
     return cudaGetLastError();
 }
 static inline size_t keyed_bucket_words(uint32_t n_keys) { return ((size_t)n_keys + 1 + 3) & ~(size_t)3; }     // keeps what follows 16-byte aligned
-size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n) { return (keyed_bucket_words(n_keys) + (size_t)n) * 4; }
-// scratch_perm: ed_keyed_scratch_bytes(n_keys, n) bytes, 16-byte aligned (bucket[n_keys + 1] then perm[n]), or nullptr = credential order
+size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n) { return (size_t)n * 96 + (4 + keyed_bucket_words(n_keys) + (size_t)n) * 4; }
+// scratch_perm: ed_keyed_scratch_bytes(n_keys, n) bytes, 32-byte aligned (pts[3 n] field elements, 4 counter words, bucket[n_keys + 1], perm[n]), or
+// nullptr = credential order and the one-thread kernel
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                                   uint8_t* ok, uint32_t* scratch_k, uint32_t* scratch_perm, cudaStream_t s, LaunchLog* lg) {
     if (n == 0) return cudaSuccess;
     const uint32_t* perm = nullptr;
+    fe* pts = (fe*)scratch_perm;
+    const int quad = scratch_perm ? quad_mode() : 0;
     if (scratch_perm && n >= 4096) {                     // small batches: one wave anyway, the three extra launches would cost more
-        uint32_t* bucket = scratch_perm;
-        uint32_t* perm_w = scratch_perm + keyed_bucket_words(n_keys);
+        uint32_t* bucket = scratch_perm + (size_t)n * 24 + 4;
+        uint32_t* perm_w = bucket + keyed_bucket_words(n_keys);
         AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for(((uint64_t)n_keys + 4) / 4, 256), 256, 0, s>>>(bucket, 0u, (uint64_t)n_keys + 1));
         AFC_LAUNCH(lg, "k_ks_hist", s, k_ks_hist<<<blocks_for(n, 256), 256, 0, s>>>(key_index, n_keys, n, bucket));
         AFC_LAUNCH(lg, "k_ks_scan", s, k_ks_scan<<<1, 1024, 0, s>>>(bucket, n_keys + 1));
         AFC_LAUNCH(lg, "k_ks_scatter", s, k_ks_scatter<<<blocks_for(n, 256), 256, 0, s>>>(key_index, n_keys, n, bucket, perm_w));
         perm = perm_w;
+    }
+    if (quad) {
+        uint32_t* tile_ctr = scratch_perm + (size_t)n * 24;
+        AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(tile_ctr, 0u, 4));
+        const QuadKeyed src{(const ge_precomp*)tabs, valid, key_pks, key_index, n_keys, perm, n};
+        if (quad == 2) AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadKeyed, true><<<quad_grid(n), QD_THREADS, 0, s>>>(src, (const ge_precomp*)comb, sigs, msgs, off, scratch_k, pts, ok, tile_ctr, quad_sms())));
+        else {
+            AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
+            AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadKeyed, false><<<quad_grid(n), QD_THREADS, 0, s>>>(src, (const ge_precomp*)comb, sigs, msgs, off, scratch_k, pts, ok, tile_ctr, quad_sms())));
+        }
+        AFC_LAUNCH(lg, "k_ed_quad_finish", s, k_ed_quad_finish<QuadKeyed><<<blocks_for(((uint64_t)n + QF_G - 1) / QF_G, QF_THREADS), QF_THREADS, 0, s>>>(src, pts, sigs, ok));
+        return cudaGetLastError();
     }
     AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
     const int G = pick_group(n, (const void*)k_ed_verify_keyed);

@@ -496,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline + cfg4 only (quick A/B runs)")
+    ap.add_argument("--ab", action="store_true", help="headline + warm_keycache + keyed only (kernel A/B runs)")
     ap.add_argument("--soak", type=float, default=0.0, help="BASELINE configs[4]: sustained mixed ingest for this many seconds (own JSON line)")
     ap.add_argument("--soak-rate", type=float, default=100_000.0, help="whole-job target rate of --soak, actions/s")
     ap.add_argument("--extras", action="store_true", help="also time sign / canonical form / microbenchmarks")
@@ -645,7 +646,7 @@ def main():
     # ---------------- roofline of the dominant kernel
     hbm_peak, peak_src = peaks()
     zero = {"avg_ms": float("nan"), "count": 0, "total_ms": 0.0}
-    dom = "k_ed_verify_cached" if prof.get("k_ed_verify_cached", zero)["total_ms"] > prof.get("k_ed_verify", zero)["total_ms"] else "k_ed_verify"
+    dom = max(("k_ed_verify_quad", "k_ed_verify_cached", "k_ed_verify"), key=lambda k: prof.get(k, zero)["total_ms"])
     kv = prof.get(dom, zero)
     achieved = ALGO_BYTES * n / (kv["avg_ms"] * 1e-3) / 1e9 if kv["count"] else float("nan")
     traffic, traffic_src = None, None
@@ -686,7 +687,7 @@ def main():
 
     # ---------------- BASELINE configs[3]: 2^22 sign + audit append sharded over the ranks, NCCL all-gather of the roots
     try:
-        line["cfg4"] = cfg4_block(ctx, dev, rank, world, barrier)
+        line["cfg4"] = cfg4_block(ctx, dev, rank, world, barrier) if not args.ab else {"skipped": "--ab"}
     except Exception as ex:
         line["cfg4"] = {"error": repr(ex)}
     torch.cuda.empty_cache()
@@ -708,6 +709,8 @@ def main():
         kc_info["cold_first_call_ms"] = cold_ms       # first call on an empty cache (1 M credentials, 1024 tables built inside it)
         line["keycache"] = kc_info
         try:
+            if args.ab:
+                raise RuntimeError("skipped (--ab)")
             ctx.keycache_configure(0)
             for _ in range(2):
                 ctx.verify_dev(d_pks, d_sigs, d_msgs, d_off, n, d_ok)
@@ -746,7 +749,7 @@ def main():
             line["keyed"] = {"error": repr(ex)}
         del d_pks, d_sigs, d_msgs, d_off, d_ok
         torch.cuda.empty_cache()
-        if world == 1:
+        if world == 1 and not args.ab:
             try:
                 line["issuer_mix"] = issuer_mix_block(ctx, dev, rank, max(3, min(args.steps, 10)))
             except Exception as ex:

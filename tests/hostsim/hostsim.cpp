@@ -205,9 +205,47 @@ void hs_fe_op(int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32])
     case 2: fe_add(r, x, y); break;
     case 3: fe_sub(r, x, y); break;
     case 4: fe_invert(r, x); break;
+    case 5: fe_addsub_m(r, x, y, 0xffffffffu, 0u); break;            // x + y
+    case 6: fe_addsub_m(r, x, y, 0xffffffffu, 0xffffffffu); break;   // x - y
+    case 7: fe_addsub_m(r, x, y, 0u, 0xffffffffu); break;            // x - 0
     default: r = x; break;
     }
     uint32_t w[8]; fe_towords(w, r); bytes_from_words(out, w, 8);
+}
+// The four-lane mixed addition of k_ed_verify_quad replayed lane by lane (ge_quad_plan is the data the kernel runs on): starting
+// from [s]B, `steps` additions of table entries chosen by the bytes of `digits` (signed, 0 = neutral entry), against
+// ge_maddsub + ge_p1p1_to_p3.  Returns the number of differing words (canonical forms of X/Z, Y/Z, T/Z compared).
+int hs_quad_madd_mismatches(const uint8_t s32[32], const int8_t* digits, int steps) {
+    ensure_tables();
+    uint32_t sw[8]; words_from_bytes(sw, s32, 8);
+    ge_p3 P; ge_scalarmult_base(P, sw, &g_comb[0]);
+    fe C[4] = {P.X, P.Y, P.Z, P.T};
+    for (int st = 0; st < steps; st++) {
+        const int d = digits[st], neg = d < 0, m = neg ? -d : d;
+        const ge_precomp* e = &g_comb[(size_t)(st % BASE_ROWS) * BASE_COLS + (m ? m - 1 : 0)];
+        if (m) { ge_p1p1 t; ge_maddsub(t, P, *e, neg); ge_p1p1_to_p3(P, t); }
+        fe u[4], mm[4], w[4], nc[4];
+        for (int r = 0; r < 4; r++) { quad_plan q = ge_quad_plan(r, neg); fe_addsub_m(u[r], C[r], C[q.src1], q.keep1, q.sgn1); }
+        for (int r = 0; r < 4; r++) {
+            quad_plan q = ge_quad_plan(r, neg);
+            fe v; ge_quad_neutral(v, r);
+            if (m && q.v_load) memcpy(v.v, (const uint8_t*)e + q.v_off, 32);
+            fe_mul(mm[r], u[r], v);
+        }
+        for (int r = 0; r < 4; r++) { quad_plan q = ge_quad_plan(r, neg); fe_addsub_m(w[r], mm[q.srcA2], mm[q.srcB2], 0xffffffffu, q.sgn2); }
+        for (int r = 0; r < 4; r++) { quad_plan q = ge_quad_plan(r, neg); fe_mul(nc[r], w[r], w[q.src3]); }
+        for (int r = 0; r < 4; r++) C[r] = nc[r];
+    }
+    // same point <=> same affine coordinates (the two chains differ by projective factors: digit 0 scales the quad's point)
+    fe zi, zj, a, b; int bad = 0;
+    fe_invert(zi, C[2]); fe_invert(zj, P.Z);
+    const fe* got[3] = {&C[0], &C[1], &C[3]}; const fe* want[3] = {&P.X, &P.Y, &P.T};
+    for (int k = 0; k < 3; k++) {
+        uint32_t wa[8], wb[8];
+        fe_mul(a, *got[k], zi); fe_mul(b, *want[k], zj); fe_towords(wa, a); fe_towords(wb, b);
+        for (int i = 0; i < 8; i++) bad += wa[i] != wb[i];
+    }
+    return bad;
 }
 int hs_verify(const uint8_t pk[32], const uint8_t* msg, uint64_t len, const uint8_t sig[64]) {
     ensure_tables();

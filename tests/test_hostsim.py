@@ -272,3 +272,24 @@ def test_constant_time_base_multiplication_equals_variable_time(hostsim):
     cases += [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(40)]
     for c in cases:
         assert hostsim.hs_scalarmult_ct_mismatches(c) == 0, c.hex()
+
+
+def test_quad_lane_mixed_addition_plan(hostsim):
+    """The data the four-lane kernel runs on (ge_quad_plan: who shuffles what from whom, which sign) replayed on the CPU against the
+    one-thread mixed addition, and the one-instruction-stream add/subtract against Python integers."""
+    rng = np.random.default_rng(44)
+    q = 2**255 - 19
+    edge = [0, 1, 37, 38, 39, 2**256 - 1, 2**256 - 38, 2**256 - 39, q, q - 1, q + 1, 2**255, 19]
+    vals = edge + [int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") for _ in range(60)]
+    for a in vals:
+        for b in vals:
+            for op, want in ((5, a + b), (6, a - b), (7, a)):
+                o = _b(32); hostsim.hs_fe_op(op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
+                assert int.from_bytes(bytes(o), "little") == want % q, (op, a, b)
+    for trial in range(6):
+        steps = 48
+        d = rng.integers(-128, 128, steps, dtype=np.int8)
+        d[rng.integers(0, steps, 5)] = 0
+        d[0] = [0, 1, -1, 127, -128, 5][trial]
+        s = rng.integers(0, 256, 32, dtype=np.uint8); s[31] &= 0x0f
+        assert hostsim.hs_quad_madd_mismatches(s.tobytes(), d.ctypes.data_as(C.POINTER(C.c_int8)), steps) == 0, trial
