@@ -148,7 +148,7 @@ func (d *device) pack(msgs [][]byte, aItem, bItem, outItem int) *packed {
 	oB := oA + align16(n*aItem)
 	oM := oB + align16(n*bItem)
 	oOut := oM + align16(total+1)
-	size := oOut + align16(n*outItem)
+	size := oOut + align16(n*outItem+1) // +1: &base[oOut] must exist even when the call has no fixed-size output (the HMAC key pack)
 	p, class := d.get(size)
 	if p == nil {
 		return nil
