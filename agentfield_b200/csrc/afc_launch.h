@@ -128,6 +128,7 @@ size_t ed_key_table_bytes(uint32_t n_keys);
 size_t ed_key_bases_bytes(uint32_t n_keys);     // scratch for ed_build_key_tables
 cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs, uint8_t* valid, void* bases_scratch, cudaStream_t s, LaunchLog* lg);
 size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n);
+size_t ed_verify_pts_bytes(uint64_t n);         // KeyCache::pts for a call of n credentials (0 unless AFC_VERIFY_QUAD is set)
 // scratch_perm: ed_keyed_scratch_bytes() bytes, 32-byte aligned: projective results, then the issuer-bucketed order (nullptr = credential order, one-thread kernel)
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,

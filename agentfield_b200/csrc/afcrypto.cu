@@ -222,7 +222,7 @@ const launch::KeyCache* kc_prepare(afc_ctx* ctx, uint32_t n) {
         if (cap > 0x80000000ull) { ctx->kc_call_cap = 0; return nullptr; }                    // beyond the 32-bit tables: generic kernel
         bool ok = dmalloc(&k.bslots, (size_t)cap * 4) && dmalloc(&k.rep, want * 4) && dmalloc(&k.kid, want * 4) && dmalloc(&k.cnt, want * 4) &&
                   dmalloc(&k.dlist, want * 4) && dmalloc(&k.cand, want * 4) && dmalloc(&k.perm, want * 4) && dmalloc(&k.cold, want * 4) &&
-                  dmalloc(&k.pts, want * 96);
+                  (launch::ed_verify_pts_bytes(want) == 0 || dmalloc(&k.pts, launch::ed_verify_pts_bytes(want)));
         if (!ok) { cudaGetLastError(); kc_free_call_buffers(k); ctx->kc_call_cap = 0; return nullptr; }
         k.bmask = (uint32_t)(cap - 1); ctx->kc_call_cap = (uint32_t)(want > 0xffffffffull ? 0xffffffffu : want);
     }

@@ -174,6 +174,61 @@ __device__ __forceinline__ void table_verify_group(Item item, Lookup lookup, con
     }
 }
 
+// The same work handed out by a counter instead of by position: every warp of a PERSISTENT grid (one CTA per resident slot) takes
+// 32 consecutive positions of the order at a time until none are left, up to KC_GMAX per group, then shares the group's inversion.
+// A static split runs in whole waves — 1 M credentials at G = 7 are 1.9 waves of the 75 776 resident threads, the last one 88 %
+// full, and G is held down to make the waves come out even; here every SM stays full until the counter runs dry and the groups
+// are as long as the batch allows (13 credentials per inversion instead of 7 for 1 M).
+template <class Item, class Lookup>
+__device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
+                                                     const uint32_t* __restrict__ ks, uint32_t n, uint32_t* __restrict__ counter,
+                                                     uint8_t* __restrict__ ok) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
+        uint32_t idx[KC_GMAX];
+        uint32_t good = 0;
+        int G = 0;
+#pragma unroll 1
+        for (; G < KC_GMAX; G++) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(counter, 32u);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= n) break;
+            const uint32_t p = first + (uint32_t)lane;
+            fe_0(X[G]); fe_1(Y[G]); fe_1(Z[G]);
+            idx[G] = 0xffffffffu;
+            if (p >= n) continue;
+            const uint32_t i = item(p);
+            idx[G] = i;
+            const ge_precomp* atab;
+            if (!lookup(i, atab)) continue;
+            uint32_t sig[16], k[8];
+            load_words8(sig, sigs + 64ull * i);
+            load_words8(sig + 8, sigs + 64ull * i + 32);
+            load_words8(k, (const uint8_t*)(ks + 8ull * i));
+            if (!ed25519_sig_wellformed(sig)) continue;
+            ed25519_keyed_point<FeInline>(X[G], Y[G], Z[G], sig, k, atab, base);
+            good |= 1u << G;
+        }
+        if (G == 0) return;
+        uint32_t enc[KC_GMAX][8];
+        ge_encode_group<FeInline, KC_GMAX>(enc, X, Y, Z, G);
+#pragma unroll 1
+        for (int g = 0; g < G; g++) {
+            const uint32_t i = idx[g];
+            if (i == 0xffffffffu) continue;
+            uint32_t r[8];
+            load_words8(r, sigs + 64ull * i);
+            uint32_t diff = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
+            ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
+        }
+        if (G < KC_GMAX) return;                   // the counter ran dry inside this group
+    }
+}
+
 // ---- building per-key tables --------------------------------------------------------------------------------------------
 // Two kernels per stage of rows (ge_key_chain_stage / ge_key_slice_start + ge_affine_run_fwd/bwd in afc_ge.cuh):
 //   k_kc_chain  one thread per key walks the doubling chain through the stage's rows (latency-bound: a handful of warps)
@@ -395,6 +450,19 @@ k_ed_verify_keyed(const ge_precomp* __restrict__ comb, const ge_precomp* __restr
         atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
         return true;
     }, comb, sigs, ks, n, T, G, ok);
+}
+
+__global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
+k_ed_verify_keyed_dyn(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
+                      const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
+                      const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok, const uint32_t* __restrict__ perm,
+                      uint32_t* __restrict__ counter) {
+    table_verify_dynamic([&](uint32_t p) { return perm ? perm[p] : p; }, [&](uint32_t i, const ge_precomp*& atab) {
+        uint32_t key = key_index[i];
+        if (key >= n_keys || !valid[key]) return false;
+        atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
+        return true;
+    }, comb, sigs, ks, n, counter, ok);
 }
 
 // ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
@@ -841,6 +909,19 @@ k_ed_quad_finish(Src src, const fe* __restrict__ pts, const uint8_t* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(KC_THREADS, AFC_CACHED_MINB)
+k_ed_verify_cached_dyn(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
+                       uint8_t* __restrict__ ok) {
+    const uint32_t n_hot = kc.state[KS_NHOT];
+    if (!n_hot) return;
+    table_verify_dynamic([&](uint32_t p) { return kc.perm[p]; }, [&](uint32_t i, const ge_precomp*& atab) {
+        const uint32_t id = kc.kid[kc.rep[i]];
+        if (!kc.valid[id]) return false;
+        atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
+        return true;
+    }, comb, sigs, ks, n_hot, kc.state + KS_QTILE, ok);
+}
+
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index.
 // Thread t of T signs credentials t, t + T, ... (G <= SIGN_GMAX of them, chosen per launch by pick_sign_group).  All their points — R = [r]B and, from seeds, A = [s]B —
 // are computed first and encoded with ONE field inversion (Montgomery's trick): per credential the inversion was 70 % of the
@@ -1156,6 +1237,24 @@ static int quad_mode() {
     if (m < 0) { const char* e = getenv("AFC_VERIFY_QUAD"); m = e ? atoi(e) : 0; if (m < 0 || m > 2) m = 0; }
     return m;
 }
+// AFC_VERIFY_DYNAMIC: 1 = the table-driven kernels take their credentials from a counter (persistent grid), 0 = static split
+static int dynamic_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("AFC_VERIFY_DYNAMIC"); m = e ? atoi(e) : 1; }
+    return m;
+}
+static uint32_t dynamic_grid(uint32_t n, const void* kernel, int threads) {
+    static thread_local int per_sm[2] = {0, 0};
+    const int slot = kernel == (const void*)k_ed_verify_cached_dyn ? 0 : 1;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!per_sm[slot]) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[slot], kernel, threads, 0) != cudaSuccess || per_sm[slot] < 1) { cudaGetLastError(); per_sm[slot] = AFC_CACHED_MINB; }
+    }
+    const uint32_t full = (uint32_t)(sms * per_sm[slot]), need = blocks_for(n, threads);
+    return need < full ? need : full;
+}
 static uint32_t quad_sms() {
     static thread_local int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
@@ -1257,9 +1356,13 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         } else AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadCached, false><<<quad_grid(n), QD_THREADS, 0, s>>>(src, cb, sigs, msgs, off, scratch_k, (fe*)kc.pts, ok, kc.state + KS_QTILE, quad_sms())));
         AFC_LAUNCH(lg, "k_ed_quad_finish", s, k_ed_quad_finish<QuadCached><<<blocks_for(((uint64_t)n + QF_G - 1) / QF_G, QF_THREADS), QF_THREADS, 0, s>>>(src, (const fe*)kc.pts, sigs, ok));
     } else {
-        const int G = pick_group(n, (const void*)k_ed_verify_cached);
-        const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
-        AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+        if (dynamic_mode()) {
+            AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_cached_dyn, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, ok));
+        } else {
+            const int G = pick_group(n, (const void*)k_ed_verify_cached);
+            const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
+            AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached<<<blocks_for(Tmax, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, G, ok));
+        }
     }
     launch_generic_verify(cb, pks, sigs, scratch_k, n, ok, kc.cold, kc.state + KS_NCOLD, s, lg);
     return cudaGetLastError();
@@ -1273,8 +1376,10 @@ cudaError_t ed_build_key_tables(const uint8_t* pks, uint32_t n_keys, void* tabs,
     return cudaGetLastError();
 }
 static inline size_t keyed_bucket_words(uint32_t n_keys) { return ((size_t)n_keys + 1 + 3) & ~(size_t)3; }     // keeps what follows 16-byte aligned
-size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n) { return (size_t)n * 96 + (4 + keyed_bucket_words(n_keys) + (size_t)n) * 4; }
-// scratch_perm: ed_keyed_scratch_bytes(n_keys, n) bytes, 32-byte aligned (pts[3 n] field elements, 4 counter words, bucket[n_keys + 1], perm[n]), or
+// the projective results of the four-lane kernel: only when that experiment is switched on (AFC_VERIFY_QUAD)
+size_t ed_verify_pts_bytes(uint64_t n) { return quad_mode() ? (size_t)n * 96 : 0; }
+size_t ed_keyed_scratch_bytes(uint32_t n_keys, uint32_t n) { return ed_verify_pts_bytes(n) + (4 + keyed_bucket_words(n_keys) + (size_t)n) * 4; }
+// scratch_perm: ed_keyed_scratch_bytes(n_keys, n) bytes, 32-byte aligned ([pts[3 n] field elements,] 4 counter words, bucket[n_keys + 1], perm[n]), or
 // nullptr = credential order and the one-thread kernel
 cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint8_t* valid, const uint8_t* key_pks, uint32_t n_keys,
                                   const uint32_t* key_index, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* off, uint32_t n,
@@ -1284,7 +1389,7 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
     fe* pts = (fe*)scratch_perm;
     const int quad = scratch_perm ? quad_mode() : 0;
     if (scratch_perm && n >= 4096) {                     // small batches: one wave anyway, the three extra launches would cost more
-        uint32_t* bucket = scratch_perm + (size_t)n * 24 + 4;
+        uint32_t* bucket = scratch_perm + ed_verify_pts_bytes(n) / 4 + 4;
         uint32_t* perm_w = bucket + keyed_bucket_words(n_keys);
         AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<blocks_for(((uint64_t)n_keys + 4) / 4, 256), 256, 0, s>>>(bucket, 0u, (uint64_t)n_keys + 1));
         AFC_LAUNCH(lg, "k_ks_hist", s, k_ks_hist<<<blocks_for(n, 256), 256, 0, s>>>(key_index, n_keys, n, bucket));
@@ -1293,7 +1398,7 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
         perm = perm_w;
     }
     if (quad) {
-        uint32_t* tile_ctr = scratch_perm + (size_t)n * 24;
+        uint32_t* tile_ctr = scratch_perm + ed_verify_pts_bytes(n) / 4;
         AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(tile_ctr, 0u, 4));
         const QuadKeyed src{(const ge_precomp*)tabs, valid, key_pks, key_index, n_keys, perm, n};
         if (quad == 2) AFC_LAUNCH(lg, "k_ed_verify_quad", s, (k_ed_verify_quad<QuadKeyed, true><<<quad_grid(n), QD_THREADS, 0, s>>>(src, (const ge_precomp*)comb, sigs, msgs, off, scratch_k, pts, ok, tile_ctr, quad_sms())));
@@ -1305,6 +1410,12 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
         return cudaGetLastError();
     }
     AFC_LAUNCH(lg, "k_ed_hram_keyed", s, k_ed_hram_keyed<<<blocks_for(n, ED_THREADS), ED_THREADS, 0, s>>>(key_pks, key_index, n_keys, sigs, msgs, off, n, scratch_k));
+    if (scratch_perm && dynamic_mode()) {
+        uint32_t* tile_ctr = scratch_perm + ed_verify_pts_bytes(n) / 4;
+        AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(tile_ctr, 0u, 4));
+        AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_keyed_dyn, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok, perm, tile_ctr));
+        return cudaGetLastError();
+    }
     const int G = pick_group(n, (const void*)k_ed_verify_keyed);
     const uint32_t T = (uint32_t)(((uint64_t)n + G - 1) / G);
     AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed<<<blocks_for(T, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, T, G, ok, perm));
