@@ -118,7 +118,7 @@ k_ed_verify(const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ pks
 // G in [1, KC_GMAX] so that the last wave is full and the inversion share small (1 M credentials on 148 SMs x 512 threads: G = 7,
 // 1.9 waves, 4.21 ms; fixed G = 4, 3.3 waves, 4.35 ms; a 65 536-credential chunk of a host call: G = 1, one wave).
 #ifndef AFC_KC_GMAX
-#define AFC_KC_GMAX 16
+#define AFC_KC_GMAX 32         // counter-driven kernels, 1 M credentials: 12 -> 3.56 ms, 16 -> 3.61, 24 -> 3.50, 32 -> 3.48 (a warp takes ~13 tiles; no group is cut short)
 #endif
 constexpr int KC_GMAX = AFC_KC_GMAX;
 #ifndef AFC_CACHED_MINB
@@ -179,13 +179,14 @@ __device__ __forceinline__ void table_verify_group(Item item, Lookup lookup, con
 // A static split runs in whole waves — 1 M credentials at G = 7 are 1.9 waves of the 75 776 resident threads, the last one 88 %
 // full, and G is held down to make the waves come out even; here every SM stays full until the counter runs dry and the groups
 // are as long as the batch allows (13 credentials per inversion instead of 7 for 1 M).
+// (One inversion per CTA instead of per thread — fe_invert_cta below — was measured here: 3.43 against 3.45 ms; not worth its barriers.)
 template <class Item, class Lookup>
 __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
                                                      const uint32_t* __restrict__ ks, uint32_t n, uint32_t* __restrict__ counter,
                                                      uint8_t* __restrict__ ok) {
     const int lane = threadIdx.x & 31;
     for (;;) {
-        fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX];
+        fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX], pz[KC_GMAX];        // pz[g] = Z_0 ... Z_g (Montgomery's trick)
         uint32_t idx[KC_GMAX];
         uint32_t good = 0;
         int G = 0;
@@ -198,31 +199,39 @@ __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, c
             const uint32_t p = first + (uint32_t)lane;
             fe_0(X[G]); fe_1(Y[G]); fe_1(Z[G]);
             idx[G] = 0xffffffffu;
-            if (p >= n) continue;
-            const uint32_t i = item(p);
-            idx[G] = i;
-            const ge_precomp* atab;
-            if (!lookup(i, atab)) continue;
-            uint32_t sig[16], k[8];
-            load_words8(sig, sigs + 64ull * i);
-            load_words8(sig + 8, sigs + 64ull * i + 32);
-            load_words8(k, (const uint8_t*)(ks + 8ull * i));
-            if (!ed25519_sig_wellformed(sig)) continue;
-            ed25519_keyed_point<FeInline>(X[G], Y[G], Z[G], sig, k, atab, base);
-            good |= 1u << G;
+            if (p < n) {
+                const uint32_t i = item(p);
+                idx[G] = i;
+                const ge_precomp* atab;
+                if (lookup(i, atab)) {
+                    uint32_t sig[16], k[8];
+                    load_words8(sig, sigs + 64ull * i);
+                    load_words8(sig + 8, sigs + 64ull * i + 32);
+                    load_words8(k, (const uint8_t*)(ks + 8ull * i));
+                    if (ed25519_sig_wellformed(sig)) {
+                        ed25519_keyed_point<FeInline>(X[G], Y[G], Z[G], sig, k, atab, base);
+                        good |= 1u << G;
+                    }
+                }
+            }
+            if (G == 0) fe_copy(pz[0], Z[0]); else fe_mul(pz[G], pz[G - 1], Z[G]);
         }
         if (G == 0) return;
-        uint32_t enc[KC_GMAX][8];
-        ge_encode_group<FeInline, KC_GMAX>(enc, X, Y, Z, G);
+        fe inv; fe_invert<FeInline>(inv, pz[G - 1]);
 #pragma unroll 1
-        for (int g = 0; g < G; g++) {
+        for (int g = G - 1; g >= 0; g--) {
+            fe zi, x, y;
+            if (g > 0) { fe_mul(zi, inv, pz[g - 1]); fe_mul(inv, inv, Z[g]); } else fe_copy(zi, inv);
+            fe_mul(x, X[g], zi); fe_mul(y, Y[g], zi);
             const uint32_t i = idx[g];
             if (i == 0xffffffffu) continue;
-            uint32_t r[8];
+            uint32_t enc[8], r[8];
+            fe_towords(enc, y);
+            enc[7] |= (uint32_t)fe_isnegative(x) << 31;
             load_words8(r, sigs + 64ull * i);
             uint32_t diff = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) diff |= enc[g][w] ^ r[w];
+            for (int w = 0; w < 8; w++) diff |= enc[w] ^ r[w];
             ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
         }
         if (G < KC_GMAX) return;                   // the counter ran dry inside this group

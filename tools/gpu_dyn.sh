@@ -1,7 +1,7 @@
 #!/bin/bash
 # counter-driven vs static split of the table-driven verify kernels: parity tests, then bench.py --ab for each
 mkdir -p gpurun_out/r2y
-timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -4
+[ -n "$SKIP_TESTS" ] || timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -4
 run() {
   name=$1; shift
   env "$@" timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --ab > gpurun_out/r2y/bench_$name.json 2> gpurun_out/r2y/bench_$name.err; rc=$?
@@ -14,5 +14,5 @@ except Exception as e: print('$name parse fail rc=$rc', e); print(open('gpurun_o
 PY
 }
 run dyn1 AFC_VERIFY_DYNAMIC=1
-run dyn0 AFC_VERIFY_DYNAMIC=0
+[ -n "$SKIP_DYN0" ] || run dyn0 AFC_VERIFY_DYNAMIC=0
 for v in $VARIANTS; do run $v AFC_VERIFY_DYNAMIC=1 AFC_LIB=$PWD/agentfield_b200/variants/libafcrypto_$v.so; done
