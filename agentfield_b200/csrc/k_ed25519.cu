@@ -1366,7 +1366,7 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         AFC_LAUNCH(lg, "k_ed_quad_finish", s, k_ed_quad_finish<QuadCached><<<blocks_for(((uint64_t)n + QF_G - 1) / QF_G, QF_THREADS), QF_THREADS, 0, s>>>(src, (const fe*)kc.pts, sigs, ok));
     } else {
         if (dynamic_mode()) {
-            AFC_LAUNCH(lg, "k_ed_verify_cached", s, k_ed_verify_cached_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_cached_dyn, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, ok));
+            AFC_LAUNCH(lg, "k_ed_verify_cached_dyn", s, k_ed_verify_cached_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_cached_dyn, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, ok));
         } else {
             const int G = pick_group(n, (const void*)k_ed_verify_cached);
             const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
@@ -1422,7 +1422,7 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
     if (scratch_perm && dynamic_mode()) {
         uint32_t* tile_ctr = scratch_perm + ed_verify_pts_bytes(n) / 4;
         AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(tile_ctr, 0u, 4));
-        AFC_LAUNCH(lg, "k_ed_verify_keyed", s, k_ed_verify_keyed_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_keyed_dyn, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok, perm, tile_ctr));
+        AFC_LAUNCH(lg, "k_ed_verify_keyed_dyn", s, k_ed_verify_keyed_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_keyed_dyn, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok, perm, tile_ctr));
         return cudaGetLastError();
     }
     const int G = pick_group(n, (const void*)k_ed_verify_keyed);

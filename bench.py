@@ -646,7 +646,7 @@ def main():
     # ---------------- roofline of the dominant kernel
     hbm_peak, peak_src = peaks()
     zero = {"avg_ms": float("nan"), "count": 0, "total_ms": 0.0}
-    dom = max(("k_ed_verify_quad", "k_ed_verify_cached", "k_ed_verify"), key=lambda k: prof.get(k, zero)["total_ms"])
+    dom = max(("k_ed_verify_cached_dyn", "k_ed_verify_cached", "k_ed_verify_quad", "k_ed_verify"), key=lambda k: prof.get(k, zero)["total_ms"])
     kv = prof.get(dom, zero)
     achieved = ALGO_BYTES * n / (kv["avg_ms"] * 1e-3) / 1e9 if kv["count"] else float("nan")
     traffic, traffic_src = None, None
