@@ -428,16 +428,18 @@ def test_transparent_key_cache_paths(ctx):
         ctx.keycache_configure(4096)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_four_lane_verify_kernel_same_results(mode):
-    """AFC_VERIFY_QUAD=1|2 (four lanes per credential, hashing before / fused; an experiment that is not the default)
-    must give the results of the default kernels: the Go edge set, the key-set path and every regime of the transparent cache are
-    re-run in a fresh process with the knob set (it is read once per process)."""
+@pytest.mark.parametrize("knob", ["AFC_VERIFY_DYNAMIC=0", "AFC_VERIFY_QUAD=1", "AFC_VERIFY_QUAD=2"])
+def test_alternative_verify_kernels_same_results(knob):
+    """The table-driven kernels that are not the default — the static split (AFC_VERIFY_DYNAMIC=0) and the four-lane experiment
+    (AFC_VERIFY_QUAD=1|2: hashing before / fused), DESIGN.md §4 — must give the results of the default ones: the Go edge set, the
+    key-set path and every regime of the transparent cache are re-run in a fresh process with the knob set (read once per process)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, AFC_VERIFY_QUAD=mode)
+    name, value = knob.split("=")
+    env = dict(os.environ)
+    env[name] = value
     sel = "test_golden_ed25519_edge_set_go_rules or test_keyed_verify_equals_generic_verify_and_go_rules or test_transparent_key_cache_paths or test_ed25519_random_parity_ragged"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", sel],
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
