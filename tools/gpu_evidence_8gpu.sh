@@ -14,7 +14,7 @@ try:
 except Exception as e:
     print('parse fail', e); print(open(o+'bench_8gpu.err').read()[-3000:])
 PY
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --soak 60 > $out/soak_8gpu_60s.json 2> $out/soak_8gpu_60s.err; echo "soak 8gpu rc=$?"
-tail -1 $out/soak_8gpu_60s.json | cut -c1-1600
+[ -n "$SKIP_SOAK" ] || timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --soak 60 > $out/soak_8gpu_60s.json 2> $out/soak_8gpu_60s.err; echo "soak 8gpu rc=$?"
+[ -n "$SKIP_SOAK" ] || tail -1 $out/soak_8gpu_60s.json | cut -c1-1600
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $out/ref_8gpu.json 2> $out/ref_8gpu.err; echo "ref rc=$?"; tail -1 $out/ref_8gpu.json | cut -c1-200
 ls -la $out
