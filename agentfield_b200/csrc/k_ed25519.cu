@@ -10,6 +10,9 @@
 //   k_ed_verify  R'_i = [S_i]B + [k_i](-A_i); ok_i = enc(R'_i) == R_i  (pure 32-bit IMAD/IADD3 work,
 //                ~2.9k field multiplications per credential — >99% of the time)
 // One credential per thread; fixed 4-bit windows keep all 32 lanes on one instruction stream.
+// When issuers repeat (the normal case) the second kernel is table-driven instead — per-issuer radix-256 tables built on the
+// device (k_kc_*), 48 mixed additions and no doublings per credential, credentials handed to warps by a counter
+// (k_ed_verify_cached_dyn / k_ed_verify_keyed_dyn) — and k_ed_verify only sees the keys that are too rare to deserve a table.
 #include <cstdlib>
 
 #include "afc_launch.h"
@@ -1237,8 +1240,8 @@ cudaError_t ed_build_tables(void* comb, cudaStream_t s, LaunchLog* lg) {
     AFC_LAUNCH(lg, "k_ed_build_tables", s, k_ed_build_tables<<<blocks_for((uint64_t)BASE_ROWS * BASE_COLS / BASE_CHUNK, 32), 32, 0, s>>>((ge_precomp*)comb));
     return cudaGetLastError();
 }
-// AFC_VERIFY_QUAD: 0 = one thread per credential (k_ed_verify_cached / _keyed; default), 1 = four lanes per credential after
-// k_ed_hram, 2 = four lanes per credential with the hashing fused.  Measured on B200, 1 M credentials, tables cached: 5.07 / 5.66 /
+// AFC_VERIFY_QUAD: 0 = one thread per credential (k_ed_verify_cached_dyn / _keyed_dyn; default), 1 = four lanes per credential after
+// k_ed_hram, 2 = four lanes per credential with the hashing fused.  Measured on B200, 1 M credentials, tables cached, static split: 5.07 / 5.66 /
 // 5.93 ms (the four-lane form keeps the multiplier 82 % busy instead of 77 %, but spends 8 multiplication slots on
 // the 7 products of a mixed addition and ~12 % more of the same pipe on register moves).  Kept as an experiment; same results.
 static int quad_mode() {
