@@ -285,7 +285,10 @@ AFC_HD void store_digest256(uint8_t* out, const uint32_t st[8]) {
 
 // ---------------------------------------------------------------------------------- SHA-512
 // (Moving the 64-bit adds to the FMA pipe the way AFC_FADD does for SHA-256 does not work here: ptxas splits
-// mad.wide.u32 d, a, ONE, c64 into IMAD.WIDE + IADD3 + IMAD.X, so the ALU pipe keeps its add and the FMA pipe gains two.)
+// mad.wide.u32 d, a, ONE, c64 into IMAD.WIDE + IADD3 + IMAD.X, so the ALU pipe keeps its add and the FMA pipe gains two.
+// Rotates as multiplications by 2^(32-n) from the constant bank — two IMAD + two IMAD.HI per 64-bit rotate instead of two SHF —
+// do leave the ALU pipe, but cost more than they free: k_ed_hram + verify per 1 M, 0 / 2 / 4 / 6 of a round's ten rotates moved:
+// 4.61 / 4.68 / 4.75 / 4.89 ms.)
 AFC_OUTLINE void sha512_compress(uint64_t* st, uint64_t* w) {
     uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1
