@@ -68,7 +68,10 @@ k_ed_build_ct16(const ge_precomp* __restrict__ base, ge_precomp* __restrict__ ct
     if (t < CT_ROWS * CT_COLS) ct16[t] = base[ge_ct16_source(t / CT_COLS, t % CT_COLS)];
 }
 
-__global__ void __launch_bounds__(ED_THREADS)
+#ifndef AFC_HRAM_MINB
+#define AFC_HRAM_MINB 1        // 78 registers, 6 CTAs/SM; capped to 72 / 64 registers (7 / 8 CTAs per SM): 4.62 / 4.68 ms per 1 M step against 4.61
+#endif
+__global__ void __launch_bounds__(ED_THREADS, AFC_HRAM_MINB)
 k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
           const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out, const uint32_t* __restrict__ list = nullptr,
           const uint32_t* __restrict__ n_list = nullptr) {
