@@ -68,10 +68,9 @@ k_ed_build_ct16(const ge_precomp* __restrict__ base, ge_precomp* __restrict__ ct
     if (t < CT_ROWS * CT_COLS) ct16[t] = base[ge_ct16_source(t / CT_COLS, t % CT_COLS)];
 }
 
-#ifndef AFC_HRAM_MINB
-#define AFC_HRAM_MINB 1        // 78 registers, 6 CTAs/SM; capped to 72 / 64 registers (7 / 8 CTAs per SM): 4.62 / 4.68 ms per 1 M step against 4.61
-#endif
-__global__ void __launch_bounds__(ED_THREADS, AFC_HRAM_MINB)
+// (78 registers, 6 CTAs/SM as the compiler leaves it; capped to 72 / 64 registers for 7 / 8 CTAs per SM: 4.62 / 4.68 ms per 1 M step
+// against 4.61 — and a second launch-bounds argument of 1 makes ptxas spend registers and lose a CTA: 4.65 ms)
+__global__ void __launch_bounds__(ED_THREADS)
 k_ed_hram(const uint8_t* __restrict__ pks, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ msgs,
           const uint64_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ k_out, const uint32_t* __restrict__ list = nullptr,
           const uint32_t* __restrict__ n_list = nullptr) {
@@ -261,6 +260,9 @@ __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, c
 #ifndef AFC_ROWS_MINB
 #define AFC_ROWS_MINB 2             // CTAs per SM the register budget of k_kc_rows is capped for (2 x 256 threads: <= 128 registers)
 #endif
+#ifndef AFC_ROWS_FE
+#define AFC_ROWS_FE FeInline        // multiplies of the forward / backward runs inlined: 1.03 ms per 1024 keys beside the hashing, out of line (FeCall) 1.15
+#endif
 constexpr int KR_PARTS = AFC_KEYROW_PARTS, KR_SLICE = COMB_COLS / KR_PARTS, KR_NT = AFC_ROWS_THREADS;
 
 struct KeyBuild {
@@ -387,13 +389,13 @@ k_kc_rows(KeyBuild b, int r0, int nr) {
         const uint32_t id = b.list ? b.list[pos] : pos;
         ge_p3 M; ge_cached c;
         ge_key_slice_start<FeCall, KR_PARTS>(M, c, b.bases3 + ((size_t)pos * COMB_ROWS + row) * KB_PTS, part);
-        ge_affine_run_fwd<FeCall, KR_SLICE>(X, Y, Z, Pz, M, c);
+        ge_affine_run_fwd<AFC_ROWS_FE, KR_SLICE>(X, Y, Z, Pz, M, c);
         fe_copy(q, Pz[KR_SLICE - 1]);
         out = b.tabs + ((size_t)id * COMB_ROWS + row) * COMB_COLS + part * KR_SLICE;
     }
     fe inv;
     fe_invert_cta<FeCall, KR_NT>(inv, q, tree);
-    if (live) ge_affine_run_bwd<FeCall, KR_SLICE>(out, X, Y, Z, Pz, inv);
+    if (live) ge_affine_run_bwd<AFC_ROWS_FE, KR_SLICE>(out, X, Y, Z, Pz, inv);
 }
 
 __global__ void __launch_bounds__(ED_THREADS)
