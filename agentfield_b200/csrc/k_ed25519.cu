@@ -944,6 +944,9 @@ k_ed_verify_cached_dyn(KeyCacheDev kc, const ge_precomp* __restrict__ comb, cons
 // are computed first and encoded with ONE field inversion (Montgomery's trick): per credential the inversion was 70 % of the
 // field work of a signature from an expanded key (16 mixed additions = 112 multiplications against 265) and twice that from a seed.
 constexpr int SIGN_GMAX = 8;
+#ifndef AFC_SIGN_FE
+#define AFC_SIGN_FE FeCall          // field multiplications of the signing kernels out of line; inlined (FeInline, 142 registers): 2^22 signatures + appends 37.5 ms against 35.6
+#endif
 // CT = true: `comb` is the 48 KB constant-time table (ge_scalarmult_base_ct), staged in shared memory; every scalar that is
 // multiplied here is secret (the nonce r, and the private scalar s when signing from seeds).
 template <bool CT>
@@ -981,7 +984,7 @@ k_ed_sign(const ge_precomp* __restrict__ comb_in, const uint8_t* __restrict__ ke
             ed25519_expand_scalar(sc[g], prefix, seed);
             sc_reduce256(sr, sc[g]);
             ge_p3 A;
-            base_mult<CT, FeCall>(A, sr, comb);
+            base_mult<CT, AFC_SIGN_FE>(A, sr, comb);
             fe_copy(X[G + g], A.X); fe_copy(Y[G + g], A.Y); fe_copy(Z[G + g], A.Z);
         } else {
             uint32_t kidx = key_index ? key_index[i] : (uint32_t)i;
@@ -992,11 +995,11 @@ k_ed_sign(const ge_precomp* __restrict__ comb_in, const uint8_t* __restrict__ ke
         const uint64_t o0 = off[i], o1 = off[i + 1];
         ed25519_nonce(rr[g], prefix, msgs + o0, o1 - o0);
         ge_p3 R;
-        base_mult<CT, FeCall>(R, rr[g], comb);
+        base_mult<CT, AFC_SIGN_FE>(R, rr[g], comb);
         fe_copy(X[g], R.X); fe_copy(Y[g], R.Y); fe_copy(Z[g], R.Z);
     }
     uint32_t enc[2 * SIGN_GMAX][8];
-    ge_encode_group<FeCall, 2 * SIGN_GMAX>(enc, X, Y, Z, mode == 0 ? 2 * G : G);
+    ge_encode_group<AFC_SIGN_FE, 2 * SIGN_GMAX>(enc, X, Y, Z, mode == 0 ? 2 * G : G);
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
         const uint64_t i = (uint64_t)t + (uint64_t)g * T;
@@ -1029,11 +1032,11 @@ k_ed_expand(const ge_precomp* __restrict__ comb_in, const uint8_t* __restrict__ 
         ed25519_expand_scalar(sc[g], pre[g], seed);
         sc_reduce256(sr, sc[g]);
         ge_p3 A;
-        base_mult<CT, FeCall>(A, sr, comb);
+        base_mult<CT, AFC_SIGN_FE>(A, sr, comb);
         fe_copy(X[g], A.X); fe_copy(Y[g], A.Y); fe_copy(Z[g], A.Z);
     }
     uint32_t enc[SIGN_GMAX][8];
-    ge_encode_group<FeCall, SIGN_GMAX>(enc, X, Y, Z, G);
+    ge_encode_group<AFC_SIGN_FE, SIGN_GMAX>(enc, X, Y, Z, G);
 #pragma unroll 1
     for (int g = 0; g < G; g++) {
         const uint64_t i = (uint64_t)t + (uint64_t)g * T;
