@@ -1272,7 +1272,11 @@ static uint32_t dynamic_grid(uint32_t n, const void* kernel, int threads) {
     if (!per_sm[slot]) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[slot], kernel, threads, 0) != cudaSuccess || per_sm[slot] < 1) { cudaGetLastError(); per_sm[slot] = AFC_CACHED_MINB; }
     }
-    const uint32_t full = (uint32_t)(sms * per_sm[slot]), need = blocks_for(n, threads);
+    // AFC_DYN_GRID_CAP (tests): at most this many CTAs, so that a small batch already makes every warp go through several groups
+    static const uint32_t cap = [] { const char* e = getenv("AFC_DYN_GRID_CAP"); return e ? (uint32_t)strtoul(e, nullptr, 10) : 0u; }();
+    uint32_t full = (uint32_t)(sms * per_sm[slot]);
+    if (cap && cap < full) full = cap;
+    const uint32_t need = blocks_for(n, threads);
     return need < full ? need : full;
 }
 static uint32_t quad_sms() {

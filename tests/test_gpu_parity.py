@@ -428,11 +428,13 @@ def test_transparent_key_cache_paths(ctx):
         ctx.keycache_configure(4096)
 
 
-@pytest.mark.parametrize("knob", ["AFC_VERIFY_DYNAMIC=0", "AFC_VERIFY_QUAD=1", "AFC_VERIFY_QUAD=2"])
+@pytest.mark.parametrize("knob", ["AFC_DYN_GRID_CAP=1", "AFC_VERIFY_DYNAMIC=0", "AFC_VERIFY_QUAD=1", "AFC_VERIFY_QUAD=2"])
 def test_alternative_verify_kernels_same_results(knob):
     """The table-driven kernels that are not the default — the static split (AFC_VERIFY_DYNAMIC=0) and the four-lane experiment
     (AFC_VERIFY_QUAD=1|2: hashing before / fused), DESIGN.md §4 — must give the results of the default ones: the Go edge set, the
-    key-set path and every regime of the transparent cache are re-run in a fresh process with the knob set (read once per process)."""
+    key-set path and every regime of the transparent cache are re-run in a fresh process with the knob set (read once per process).
+    AFC_DYN_GRID_CAP=1 runs the default, counter-driven kernels on ONE CTA: a warp then goes through several groups of 32 tiles
+    with 12 000 credentials, the path a full grid only takes beyond 2.4 M credentials per call."""
     import os
     import subprocess
     import sys
@@ -996,6 +998,48 @@ def test_full_size_verify_properties_config2(ctx):
     for _ in range(2):
         got = ctx.verify_packed(pk_h, sg_h, ms_h, off_h)
         assert (np.asarray(got).astype(np.uint8) == expect[:nh].cpu().numpy()).all()
+
+
+def test_three_million_credentials_cross_the_group_boundary(ctx):
+    """The counter-driven table kernels run groups of up to 32 tiles per warp; a full grid (75 776 threads on a B200) only starts a
+    SECOND group beyond 2.4 M credentials in one launch.  3 M short credentials from 2048 keys, 1 in 64 corrupted, through the
+    transparent cache and the key-set path: the bitmap must equal the corruption pattern exactly."""
+    import torch
+    from agentfield_b200 import KeySet
+    n, K, L = 3_000_000, 2048, 48
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xAF66)
+    d_msgs = torch.randint(0, 256, (n, L), dtype=torch.uint8, device=dev, generator=g)
+    d_kseeds = torch.randint(0, 256, (K, 32), dtype=torch.uint8, device=dev, generator=g)
+    d_exp = torch.empty((K, 96), dtype=torch.uint8, device=dev)
+    ctx.expand_dev(d_kseeds, K, d_exp)
+    d_ki = ((torch.arange(n, device=dev) * 7919) % K).to(torch.int32)
+    d_off = (torch.arange(n + 1, device=dev, dtype=torch.int64) * L)
+    d_sigs = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    ctx.sign_expanded_dev(d_exp, d_ki, d_msgs.view(-1), d_off, n, d_sigs)
+    idx = torch.arange(n, device=dev)
+    bad_m, bad_r = idx % 64 == 5, idx % 64 == 37
+    d_msgs[idx[bad_m], 3] ^= 0x10
+    d_sigs[idx[bad_r], 7] ^= 0x01
+    expect = (~(bad_m | bad_r)).to(torch.uint8)
+    d_pks = d_exp[:, 64:][d_ki.long()].contiguous()
+    d_ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+    for _ in range(2):                                            # cold (tables built inside the call), then cached
+        d_ok.zero_()
+        ctx.verify_dev(d_pks, d_sigs, d_msgs.view(-1), d_off, n, d_ok)
+        torch.cuda.synchronize()
+        assert torch.equal(d_ok, expect)
+    ks = KeySet([bytes(p) for p in d_exp[:, 64:].cpu().numpy()], ctx)
+    d_ok.zero_()
+    ks.verify_dev(d_ki, d_sigs, d_msgs.view(-1), d_off, n, d_ok)
+    torch.cuda.synchronize()
+    assert torch.equal(d_ok, expect)
+    ks.close()
+    # and a sample against the oracle, so that the signatures themselves are not taken on trust
+    sample = [0, 1, 5, 37, 63, 64, n // 2, n - 1, 2_424_833, 2_900_001]
+    pk_h, sg_h, ms_h = d_pks[sample].cpu().numpy(), d_sigs[sample].cpu().numpy(), d_msgs[sample].cpu().numpy()
+    for j, i in enumerate(sample):
+        assert CO.verify(pk_h[j].tobytes(), ms_h[j].tobytes(), sg_h[j].tobytes()) == bool(expect[i].item()), i
 
 
 def test_full_size_hmac_properties_config3(ctx):
