@@ -87,6 +87,34 @@ AFC_HD void ge_load_precomp(ge_precomp& e, const ge_precomp* src) {
     e = *src;
 #endif
 }
+// The same entry already arranged for subtraction when neg != 0 — ypx and ymx change places at LOAD time (an address, not 16
+// selects per addition); what is left of the sign is the exchange of the two outputs in ge_madd_arranged.
+AFC_HD void ge_load_precomp_arranged(ge_precomp& e, const ge_precomp* src, int neg) {
+#if AFC_DEVICE_CODE && AFC_TABLE_LOAD256
+    const uint32_t* p = (const uint32_t*)src;
+    const uint32_t* pa = p + (neg ? 8 : 0);
+    const uint32_t* pb = p + (neg ? 0 : 8);
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.ypx.v[0]), "=r"(e.ypx.v[1]), "=r"(e.ypx.v[2]), "=r"(e.ypx.v[3]), "=r"(e.ypx.v[4]), "=r"(e.ypx.v[5]), "=r"(e.ypx.v[6]), "=r"(e.ypx.v[7]) : "l"(pa));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.ymx.v[0]), "=r"(e.ymx.v[1]), "=r"(e.ymx.v[2]), "=r"(e.ymx.v[3]), "=r"(e.ymx.v[4]), "=r"(e.ymx.v[5]), "=r"(e.ymx.v[6]), "=r"(e.ymx.v[7]) : "l"(pb));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.xy2d.v[0]), "=r"(e.xy2d.v[1]), "=r"(e.xy2d.v[2]), "=r"(e.xy2d.v[3]), "=r"(e.xy2d.v[4]), "=r"(e.xy2d.v[5]), "=r"(e.xy2d.v[6]), "=r"(e.xy2d.v[7]) : "l"(p + 16));
+#else
+    e = *src;
+    if (neg) { fe t = e.ypx; e.ypx = e.ymx; e.ymx = t; }
+#endif
+}
+template <class F = FeInline>
+AFC_HD void ge_madd_arranged(ge_p1p1& r, const ge_p3& p, const ge_precomp& q, int neg) {
+    fe a, b, c, d;
+    fe_add(a, p.Y, p.X); fe_sub(b, p.Y, p.X);
+    F::mul(a, a, q.ypx); F::mul(b, b, q.ymx); F::mul(c, q.xy2d, p.T); fe_dbl(d, p.Z);
+    fe_sub(r.X, a, b); fe_add(r.Y, a, b);
+    fe dpc, dmc;
+    fe_add(dpc, d, c); fe_sub(dmc, d, c);
+    fe_select(r.Z, dpc, dmc, neg); fe_select(r.T, dmc, dpc, neg);
+}
 // mixed addition with an affine precomputed point
 template <class F = FeInline>
 AFC_HD void ge_maddsub(ge_p1p1& r, const ge_p3& p, const ge_precomp& q, int neg) {
@@ -586,6 +614,9 @@ AFC_HD int ge_build_key_row(ge_precomp* row, const uint32_t* pk, int i) {
 #ifndef AFC_KP_PREFETCH
 #define AFC_KP_PREFETCH 1
 #endif
+#ifndef AFC_KP_ARRANGED
+#define AFC_KP_ARRANGED 1        // table entries loaded already arranged for the digit's sign (ge_load_precomp_arranged): 3.45 -> 3.42 ms per 1 M
+#endif
 #define AFC_PF_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define AFC_PF_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #if AFC_KP_PREFETCH == 2
@@ -625,15 +656,25 @@ AFC_HD void ed25519_keyed_point(fe& X, fe& Y, fe& Z, const uint32_t* sig, const 
         if (dk != 0) {
             int neg = dk < 0, m = neg ? -dk : dk;
             ge_precomp e;
+#if AFC_KP_ARRANGED
+            ge_load_precomp_arranged(e, &atab[i * COMB_COLS + (m - 1)], neg);
+            ge_madd_arranged<F>(t, h, e, neg);
+#else
             ge_load_precomp(e, &atab[i * COMB_COLS + (m - 1)]);
             ge_maddsub<F>(t, h, e, neg);
+#endif
             ge_p1p1_to_p3<F>(h, t);
         }
         if (ds != 0) {
             int neg = ds < 0, m = neg ? -ds : ds;
             ge_precomp e;
+#if AFC_KP_ARRANGED
+            ge_load_precomp_arranged(e, &base[(size_t)(i >> SH) * BASE_COLS + (m - 1)], neg);
+            ge_madd_arranged<F>(t, h, e, neg);
+#else
             ge_load_precomp(e, &base[(size_t)(i >> SH) * BASE_COLS + (m - 1)]);
             ge_maddsub<F>(t, h, e, neg);
+#endif
             ge_p1p1_to_p3<F>(h, t);
         }
     }
