@@ -184,11 +184,15 @@ __device__ __forceinline__ void table_verify_group(Item item, Lookup lookup, con
 // A static split runs in whole waves — 1 M credentials at G = 7 are 1.9 waves of the 75 776 resident threads, the last one 88 %
 // full, and G is held down to make the waves come out even; here every SM stays full until the counter runs dry and the groups
 // are as long as the batch allows (13 credentials per inversion instead of 7 for 1 M).
-// (One inversion per CTA instead of per thread — fe_invert_cta below — was measured here: 3.43 against 3.45 ms; not worth its barriers.)
-template <class Item, class Lookup>
+// The inversion is shared by the whole CTA (product tree in shared memory, fe_invert_cta below): at 1 M credentials a thread has
+// ~13 of its own to share one with and the CTA-wide form buys 0.5 %; in a 65 536-credential chunk of a host call a warp gets ONE
+// tile, and an inversion per credential would be a third of the work (0.41 -> 0.29 ms).
+template <class F, int NT> __device__ __forceinline__ void fe_invert_cta(fe& inv, const fe& q, fe* tree);
+template <int NT, class Item, class Lookup>
 __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, const ge_precomp* __restrict__ base, const uint8_t* __restrict__ sigs,
                                                      const uint32_t* __restrict__ ks, uint32_t n, uint32_t* __restrict__ counter,
-                                                     uint8_t* __restrict__ ok) {
+                                                     uint8_t* __restrict__ ok, int share_inv) {
+    __shared__ fe tree[2 * NT];
     const int lane = threadIdx.x & 31;
     for (;;) {
         fe X[KC_GMAX], Y[KC_GMAX], Z[KC_GMAX], pz[KC_GMAX];        // pz[g] = Z_0 ... Z_g (Montgomery's trick)
@@ -221,8 +225,10 @@ __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, c
             }
             if (G == 0) fe_copy(pz[0], Z[0]); else fe_mul(pz[G], pz[G - 1], Z[G]);
         }
-        if (G == 0) return;
-        fe inv; fe_invert<FeInline>(inv, pz[G - 1]);
+        fe inv, q;
+        if (G) fe_copy(q, pz[G - 1]); else fe_1(q);                  // a warp that found the counter dry still takes part in the tree
+        if (share_inv) fe_invert_cta<FeCall, NT>(inv, q, tree);
+        else fe_invert<FeCall>(inv, q);                              // small launch, idle SMs: redundant inversions in parallel are the shorter path
 #pragma unroll 1
         for (int g = G - 1; g >= 0; g--) {
             fe zi, x, y;
@@ -239,7 +245,8 @@ __device__ __forceinline__ void table_verify_dynamic(Item item, Lookup lookup, c
             for (int w = 0; w < 8; w++) diff |= enc[w] ^ r[w];
             ok[i] = (uint8_t)(((good >> g) & 1u) && diff == 0);
         }
-        if (G < KC_GMAX) return;                   // the counter ran dry inside this group
+        if (share_inv) { if (!__syncthreads_or(G == KC_GMAX)) return; }     // every warp saw the counter run dry (and nobody still reads the tree)
+        else if (G < KC_GMAX) return;
     }
 }
 
@@ -473,13 +480,13 @@ __global__ void __launch_bounds__(ED_THREADS, AFC_CACHED_MINB)
 k_ed_verify_keyed_dyn(const ge_precomp* __restrict__ comb, const ge_precomp* __restrict__ tabs, const uint8_t* __restrict__ valid,
                       const uint32_t* __restrict__ key_index, uint32_t n_keys, const uint8_t* __restrict__ sigs,
                       const uint32_t* __restrict__ ks, uint32_t n, uint8_t* __restrict__ ok, const uint32_t* __restrict__ perm,
-                      uint32_t* __restrict__ counter) {
-    table_verify_dynamic([&](uint32_t p) { return perm ? perm[p] : p; }, [&](uint32_t i, const ge_precomp*& atab) {
+                      uint32_t* __restrict__ counter, int share_inv) {
+    table_verify_dynamic<ED_THREADS>([&](uint32_t p) { return perm ? perm[p] : p; }, [&](uint32_t i, const ge_precomp*& atab) {
         uint32_t key = key_index[i];
         if (key >= n_keys || !valid[key]) return false;
         atab = tabs + (size_t)key * COMB_ROWS * COMB_COLS;
         return true;
-    }, comb, sigs, ks, n, counter, ok);
+    }, comb, sigs, ks, n, counter, ok, share_inv);
 }
 
 // ---- transparent issuer-key cache behind afc_ed25519_verify_batch -----------------------------------------------
@@ -928,15 +935,15 @@ k_ed_quad_finish(Src src, const fe* __restrict__ pts, const uint8_t* __restrict_
 
 __global__ void __launch_bounds__(KC_THREADS, AFC_CACHED_MINB)
 k_ed_verify_cached_dyn(KeyCacheDev kc, const ge_precomp* __restrict__ comb, const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ ks,
-                       uint8_t* __restrict__ ok) {
+                       uint8_t* __restrict__ ok, int share_inv) {
     const uint32_t n_hot = kc.state[KS_NHOT];
     if (!n_hot) return;
-    table_verify_dynamic([&](uint32_t p) { return kc.perm[p]; }, [&](uint32_t i, const ge_precomp*& atab) {
+    table_verify_dynamic<KC_THREADS>([&](uint32_t p) { return kc.perm[p]; }, [&](uint32_t i, const ge_precomp*& atab) {
         const uint32_t id = kc.kid[kc.rep[i]];
         if (!kc.valid[id]) return false;
         atab = (const ge_precomp*)kc.tabs + (size_t)id * COMB_ROWS * COMB_COLS;
         return true;
-    }, comb, sigs, ks, n_hot, kc.state + KS_QTILE, ok);
+    }, comb, sigs, ks, n_hot, kc.state + KS_QTILE, ok, share_inv);
 }
 
 // mode 0: seeds (32 B each) -> expand then sign;  mode 1: expanded keys (96 B each) selected by key_index.
@@ -1279,6 +1286,9 @@ static uint32_t dynamic_grid(uint32_t n, const void* kernel, int threads) {
     const uint32_t need = blocks_for(n, threads);
     return need < full ? need : full;
 }
+// one inversion per CTA (less work) or per thread (shorter critical path): 16 384 credentials 0.31 ms per thread, 0.33 per CTA;
+// 65 536: 0.56 / 0.54; 1 M: 3.42 / 3.39
+static int dynamic_share_inv(uint32_t n) { return n > 32768u; }
 static uint32_t quad_sms() {
     static thread_local int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
@@ -1381,7 +1391,7 @@ cudaError_t ed_verify_batch(const void* comb, const uint8_t* pks, const uint8_t*
         AFC_LAUNCH(lg, "k_ed_quad_finish", s, k_ed_quad_finish<QuadCached><<<blocks_for(((uint64_t)n + QF_G - 1) / QF_G, QF_THREADS), QF_THREADS, 0, s>>>(src, (const fe*)kc.pts, sigs, ok));
     } else {
         if (dynamic_mode()) {
-            AFC_LAUNCH(lg, "k_ed_verify_cached_dyn", s, k_ed_verify_cached_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_cached_dyn, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, ok));
+            AFC_LAUNCH(lg, "k_ed_verify_cached_dyn", s, k_ed_verify_cached_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_cached_dyn, KC_THREADS), KC_THREADS, 0, s>>>(kc, cb, sigs, scratch_k, ok, dynamic_share_inv(n)));
         } else {
             const int G = pick_group(n, (const void*)k_ed_verify_cached);
             const uint32_t Tmax = (uint32_t)(((uint64_t)n + G - 1) / G);
@@ -1437,7 +1447,7 @@ cudaError_t ed_verify_keyed_batch(const void* comb, const void* tabs, const uint
     if (scratch_perm && dynamic_mode()) {
         uint32_t* tile_ctr = scratch_perm + ed_verify_pts_bytes(n) / 4;
         AFC_LAUNCH(lg, "k_fill_u32", s, k_fill_u32<<<1, 256, 0, s>>>(tile_ctr, 0u, 4));
-        AFC_LAUNCH(lg, "k_ed_verify_keyed_dyn", s, k_ed_verify_keyed_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_keyed_dyn, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok, perm, tile_ctr));
+        AFC_LAUNCH(lg, "k_ed_verify_keyed_dyn", s, k_ed_verify_keyed_dyn<<<dynamic_grid(n, (const void*)k_ed_verify_keyed_dyn, ED_THREADS), ED_THREADS, 0, s>>>((const ge_precomp*)comb, (const ge_precomp*)tabs, valid, key_index, n_keys, sigs, scratch_k, n, ok, perm, tile_ctr, dynamic_share_inv(n)));
         return cudaGetLastError();
     }
     const int G = pick_group(n, (const void*)k_ed_verify_keyed);
